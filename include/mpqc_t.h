@@ -1,0 +1,137 @@
+/*
+ * mpqc_t.h -- C ABI of libmpqc_t_cuda.so: the B200 (sm_100a) implementation of the
+ * closed-shell CCSD perturbative-triples (T) energy correction.
+ *
+ * This is the drop-in boundary for MPQC4's  CCSD_T<Tile,Policy>::compute_ccsd_t()
+ *   /root/reference/src/mpqc/chemistry/qc/lcao/cc/ccsd_t.h:144-177  (dispatcher)
+ *   /root/reference/src/mpqc/chemistry/qc/lcao/cc/ccsd_t.h:200-711  (coarse, the default)
+ *   /root/reference/src/mpqc/chemistry/qc/lcao/cc/ccsd_t.h:1127-1170 (straight)
+ * i.e. everything between "T1/T2, orbital energies and the three integral classes are in hand"
+ * and "a double comes back".  The MPQC-side adapter that gathers the TiledArray objects into the
+ * dense buffers below is integration/ccsd_t_gpu.h.
+ *
+ * Plain pointers and sizes only; no C++ or torch types; no exception crosses this boundary.
+ * All arrays are IEEE double, dense, row-major (last index fastest), in exactly the layouts
+ * the reference's getters produce:
+ *
+ *   eps_occ[o]          = eps[n_frozen .. n_occ)                 ccsd_t.h:2299-2311, ccsd.h:141-148
+ *   eps_vir[v]          = eps[n_occ .. n_all)
+ *   t1    [v][o]        t1("a,i")                                ccsd.h:165-179
+ *   t2    [v][v][o][o]  t2("a,b,i,j")
+ *   g_abij[v][v][o][o]  <ij|ab>  result("a,b,i,j")               ccsd_t.h:2238-2244
+ *   g_aijk[v][o][o][o]  <ij|ka>  result("a,i,j,k")               ccsd_t.h:2210-2221
+ *   g_abci[v][v][v][o]  <ia|bc>  result("a,b,c,i")               ccsd_t.h:2224-2235
+ *
+ * Work units.  E(T) = sum over ordered occupied triples i>=j>=k (i==j==k excluded, weight 0) of
+ * w_ijk * sum_abc (W+V) Z / D, w = 2 (all distinct) or 1 (two equal).  Triples are enumerated
+ * i-major:  for i in [0,o) for j in [0,i] for k in [0,j], skipping i==j==k;  mpqc_t_triple_count(o)
+ * = o(o+1)(o+2)/6 - o.  A run processes the units  first, first+stride, ...  (count of them), which is
+ * how the path is sharded over GPUs / ranks (replaces the round-robin of ccsd_t.h:477-480).  The
+ * partial energies are summed by the caller (replaces gop.sum, ccsd_t.h:692).
+ */
+#ifndef MPQC_T_H
+#define MPQC_T_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPQC_T_ABI_VERSION 1
+
+/* status codes (mapped to mpqc::Exception subclasses by the adapter, util/core/exception.h:93-593) */
+enum {
+  MPQC_T_OK = 0,
+  MPQC_T_ERR_BAD_ARG = 1,    /* -> InputError / ProgrammingError */
+  MPQC_T_ERR_NO_DEVICE = 2,  /* -> FeatureDisabled (no CUDA device; there is NO CPU fallback) */
+  MPQC_T_ERR_OOM = 3,        /* -> MemAllocFailed */
+  MPQC_T_ERR_CUDA = 4,       /* -> ProgrammingError (CUDA runtime / driver error) */
+  MPQC_T_ERR_NCCL = 5,       /* -> ProgrammingError (NCCL error) */
+  MPQC_T_ERR_INTERNAL = 6
+};
+
+typedef struct mpqc_t_problem {
+  int64_t o;              /* active occupied   (trange1_engine()->get_active_occ(), trange1_engine.h:60-72) */
+  int64_t v;              /* virtuals          (trange1_engine()->get_vir()) */
+  const double* eps_occ;  /* [o] */
+  const double* eps_vir;  /* [v] */
+  const double* t1;       /* [v][o] */
+  const double* t2;       /* [v][v][o][o] */
+  const double* g_abij;   /* [v][v][o][o] */
+  const double* g_aijk;   /* [v][o][o][o] */
+  const double* g_abci;   /* [v][v][v][o] */
+} mpqc_t_problem;
+
+typedef struct mpqc_t_options {
+  int32_t ngpu;               /* number of devices this process drives (>=1); 0 -> 1 */
+  const int32_t* device_ids;  /* [ngpu] CUDA ordinals, NULL -> 0..ngpu-1 */
+  int32_t verbose;            /* 0 silent, 1 prints the reference's "(T) Energy: ... Time: ... S" line */
+  int32_t inputs_on_device;   /* 0: problem pointers are host memory; 1: device memory on device_ids[0] (ngpu must be 1) */
+  int64_t unit_first;         /* first triple unit of this process' shard (rank) */
+  int64_t unit_stride;        /* stride between this process' units (world size); 0 -> 1 */
+  int64_t unit_count;         /* number of units to process; <0 -> all remaining with that stride */
+  int32_t batch;              /* triples per kernel launch; 0 -> auto */
+  int32_t steal_chunk;        /* in-process multi-GPU: triples per work-stealing grab; 0 -> auto */
+  int32_t use_nccl;           /* in-process multi-GPU: sum partial E(T) with ncclAllReduce (1) or on the host (0) */
+  int32_t reserved[5];
+} mpqc_t_options;
+
+typedef struct mpqc_t_stats {
+  double seconds_total;     /* wall time of the call */
+  double seconds_upload;    /* host -> device copies */
+  double seconds_relayout;  /* integral/amplitude blocking on device (replaces ccsd_t.h:2219,2233,2242 + reblock) */
+  double seconds_compute;   /* triples loop, device-timed with CUDA events (max over devices) */
+  double seconds_contract;  /* share of seconds_compute spent in the W contraction kernel (single-GPU profile mode only, else 0) */
+  double seconds_energy;    /* share spent in the fused V/symmetrise/denominator/reduce kernel (same) */
+  double flops;             /* algorithmic: 12 v^3 (v+o) per triple processed */
+  double flops_executed;    /* including tile padding */
+  int64_t units;            /* triples processed by this call */
+  int64_t kernel_launches;  /* number of kernels launched by this call */
+  int64_t bytes_h2d;
+  int64_t bytes_d2h;
+  int32_t ngpu;
+  int32_t reserved[7];
+} mpqc_t_stats;
+
+typedef struct mpqc_t_handle mpqc_t_handle; /* opaque: one device's resident, re-laid-out problem */
+
+/* ---- one-shot entry point: what the adapter's compute_ccsd_t() calls ------------------------ */
+/* Computes this process' partial E(T) over its units (all units when unit_first=0, unit_stride=1,
+ * unit_count<0).  Caller owns every buffer for the duration of the call; nothing is retained. */
+int mpqc_t_energy(const mpqc_t_problem* p, const mpqc_t_options* opt, double* e_t, mpqc_t_stats* stats);
+
+/* ---- split-phase API (lets uploads be timed separately; used by bench.py and the tests) ------ */
+int mpqc_t_create(mpqc_t_handle** h, int64_t o, int64_t v, int32_t device);
+/* host (on_device=0) or device (on_device=1) buffers -> occupied-major operand layouts in HBM */
+int mpqc_t_upload(mpqc_t_handle* h, const mpqc_t_problem* p, int32_t on_device, mpqc_t_stats* stats);
+/* process units first, first+stride, ... (count of them; <0 = to the end).  partial_e = weighted sum
+ * over those units (summed in unit order, so any sharding gives bit-identical per-unit terms);
+ * unit_e (optional, may be NULL) receives the weighted per-unit energies [count].  batch 0 = auto. */
+int mpqc_t_run(mpqc_t_handle* h, int64_t first, int64_t stride, int64_t count, int32_t batch,
+               double* partial_e, double* unit_e, mpqc_t_stats* stats);
+/* debugging / parity aid: W^{abc}_{ijk} of one occupied triple as a dense [v][v][v] host array */
+int mpqc_t_debug_w(mpqc_t_handle* h, int32_t i, int32_t j, int32_t k, double* w_host);
+/* CUDA stream the handle launches on (cudaStream_t as void*), for event timing by the caller */
+void* mpqc_t_stream(mpqc_t_handle* h);
+int mpqc_t_destroy(mpqc_t_handle* h);
+
+/* ---- helpers ------------------------------------------------------------------------------- */
+int64_t mpqc_t_triple_count(int64_t o);
+/* unit index -> (i,j,k) of the enumeration above; returns MPQC_T_ERR_BAD_ARG when out of range */
+int mpqc_t_triple_of_unit(int64_t o, int64_t unit, int32_t* i, int32_t* j, int32_t* k);
+double mpqc_t_flops(int64_t o, int64_t v);           /* 2 o^3 v^3 (v+o), the published work model */
+double mpqc_t_unit_flops(int64_t o, int64_t v);      /* 12 v^3 (v+o) */
+int mpqc_t_device_count(void);
+const char* mpqc_t_version(void);
+const char* mpqc_t_strerror(int status);
+const char* mpqc_t_last_error(void);                 /* thread-local detail string of the last failure */
+
+/* FP64 pipe microbenchmarks used to fix the roofline denominator on the box:
+ * which = 0: DMMA.8x8x4 issue-bound loop, 1: DFMA issue-bound loop.  Returns TFLOP/s in *tflops. */
+int mpqc_t_microbench(int32_t device, int32_t which, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPQC_T_H */

@@ -1,0 +1,803 @@
+// libmpqc_t_cuda.so -- host driver + C ABI (include/mpqc_t.h) of the B200 (T) path.
+//
+// Replaces the body of CCSD_T::compute_ccsd_t() (ccsd_t.h:144-177) / compute_ccsd_t_coarse_grain
+// (ccsd_t.h:200-711): integrals and amplitudes arrive as dense buffers, are re-laid-out once into
+// occupied-major operand panels (relayout.cuh), and the (i>=j>=k) triple space is walked in batches
+// of {W-contraction DMMA kernel (w_contract.cuh) -> fused energy kernel (t_energy.cuh)}.
+// There is no CPU fallback: without a CUDA device every entry point returns MPQC_T_ERR_NO_DEVICE.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+#include "microbench.cuh"
+#include "relayout.cuh"
+#include "t_energy.cuh"
+#include "w_contract.cuh"
+
+using namespace mpqc_t;
+
+namespace {
+
+double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn* out) {
+  static EncodeTiledFn cached = nullptr;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!cached) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    MPQC_T_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    MPQC_T_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, MPQC_T_ERR_CUDA,
+                 "cuTensorMapEncodeTiled not available from the driver");
+    cached = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  *out = cached;
+  return MPQC_T_OK;
+}
+
+int encode_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box) {
+  EncodeTiledFn fn;
+  MPQC_T_TRY(get_encode_fn(&fn));
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int d = 0; d < rank; ++d) {
+    gdim[d] = dims[d];
+    bdim[d] = box[d];
+    estr[d] = 1;
+    if (d > 0) gstr[d - 1] = strides_bytes[d - 1];
+  }
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, base, gdim, gstr, bdim, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, box %u,%u,%u)", (int)r,
+             rank, box[0], box[1], rank > 2 ? box[2] : 0u);
+    return fail(MPQC_T_ERR_CUDA, buf, __FILE__, __LINE__);
+  }
+  return MPQC_T_OK;
+}
+
+int64_t roundup(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+// -------------------------------------------------------------------------------------------------
+// handle
+// -------------------------------------------------------------------------------------------------
+struct mpqc_t_handle {
+  int device = 0;
+  int64_t o = 0, v = 0, Kp = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  // resident operands
+  double *A = nullptr, *B = nullptr, *GV = nullptr, *T1T = nullptr, *eps_occ = nullptr, *eps_vir = nullptr;
+  uint8_t* tile_sets = nullptr;
+  bool uploaded = false;
+  // plan
+  int tp = 0, tq = 0, tn = 0, nfrag = 0, npt = 0, nqt = 0, nnt = 0, ldw = 0, kblocks = 0;
+  int ntile = 0, ntt = 0;
+  CUtensorMap tmA_n, tmA_t, tmB;
+  // work buffers
+  int batch_cap = 0;
+  double *W = nullptr, *partial = nullptr;
+  int64_t units_cap = 0;
+  int* triples_dev = nullptr;
+  double* unit_e_dev = nullptr;
+};
+
+namespace {
+
+void free_work(mpqc_t_handle* h) {
+  cudaFree(h->W);
+  cudaFree(h->partial);
+  h->W = h->partial = nullptr;
+  h->batch_cap = 0;
+}
+
+int plan(mpqc_t_handle* h) {
+  const int v = (int)h->v;
+  // row patch (tp x tq) of a 128-row tile: maximise useful rows, prefer odd tp (bank-conflict-free
+  // fragment reads of the transposed box, see w_contract.cuh)
+  double best = -1.0;
+  for (int tp = 1; tp <= std::min(v, kBM); ++tp) {
+    int tq = std::min(v, kBM / tp);
+    if (tq < 1) continue;
+    tq = std::min(tq, 256);
+    double tiles = std::ceil((double)v / tp) * std::ceil((double)v / tq);
+    double eff = (double)v * v / (tiles * kBM);
+    double score = eff * ((tp & 1) ? 1.0 : 0.97);
+    if (score > best + 1e-12) {
+      best = score;
+      h->tp = tp;
+      h->tq = tq;
+    }
+  }
+  h->npt = (v + h->tp - 1) / h->tp;
+  h->nqt = (v + h->tq - 1) / h->tq;
+  const int bn = kMaxNFrag * 8;
+  h->nnt = (v + bn - 1) / bn;
+  int cols = (v + h->nnt - 1) / h->nnt;
+  h->nfrag = (cols + 7) / 8;
+  h->tn = h->nfrag * 8;
+  h->ldw = (int)roundup(v, 16);
+  h->kblocks = (int)((h->Kp + kBK - 1) / kBK);
+  h->ntile = (v + kET - 1) / kET;
+  h->ntt = h->ntile * (h->ntile + 1) * (h->ntile + 2) / 6;
+  return MPQC_T_OK;
+}
+
+int make_maps(mpqc_t_handle* h) {
+  const uint64_t v = (uint64_t)h->v, o = (uint64_t)h->o, Kp = (uint64_t)h->Kp;
+  {
+    uint64_t dims[4] = {Kp, v, v, o};
+    uint64_t str[3] = {Kp * 8, v * Kp * 8, v * v * Kp * 8};
+    uint32_t box_n[4] = {(uint32_t)kBK, (uint32_t)h->tq, (uint32_t)h->tp, 1};
+    uint32_t box_t[4] = {(uint32_t)kBK, (uint32_t)h->tp, (uint32_t)h->tq, 1};
+    MPQC_T_TRY(encode_map(&h->tmA_n, h->A, 4, dims, str, box_n));
+    MPQC_T_TRY(encode_map(&h->tmA_t, h->A, 4, dims, str, box_t));
+  }
+  {
+    uint64_t dims[3] = {Kp, v, o * o};
+    uint64_t str[2] = {Kp * 8, v * Kp * 8};
+    uint32_t box[3] = {(uint32_t)kBK, (uint32_t)h->tn, 1};
+    MPQC_T_TRY(encode_map(&h->tmB, h->B, 3, dims, str, box));
+  }
+  return MPQC_T_OK;
+}
+
+int ensure_work(mpqc_t_handle* h, int batch) {
+  if (batch <= h->batch_cap) return MPQC_T_OK;
+  free_work(h);
+  size_t wbytes = (size_t)batch * 3 * h->v * h->v * h->ldw * sizeof(double);
+  MPQC_T_CUDA(cudaMalloc(&h->W, wbytes));
+  MPQC_T_CUDA(cudaMalloc(&h->partial, (size_t)batch * h->ntt * sizeof(double)));
+  h->batch_cap = batch;
+  return MPQC_T_OK;
+}
+
+int ensure_units(mpqc_t_handle* h, int64_t n) {
+  if (n <= h->units_cap) return MPQC_T_OK;
+  cudaFree(h->triples_dev);
+  cudaFree(h->unit_e_dev);
+  h->triples_dev = nullptr;
+  h->unit_e_dev = nullptr;
+  h->units_cap = 0;
+  MPQC_T_CUDA(cudaMalloc(&h->triples_dev, (size_t)n * 3 * sizeof(int)));
+  MPQC_T_CUDA(cudaMalloc(&h->unit_e_dev, (size_t)n * sizeof(double)));
+  h->units_cap = n;
+  return MPQC_T_OK;
+}
+
+int auto_batch(const mpqc_t_handle* h) {
+  int64_t tiles_per_triple = 3LL * h->npt * h->nqt * h->nnt;
+  int64_t nb = (8LL * h->num_sms + tiles_per_triple - 1) / tiles_per_triple;
+  nb = std::max<int64_t>(1, std::min<int64_t>(nb, 1024));
+  // bound the W workspace to ~6 GB
+  size_t per = (size_t)3 * h->v * h->v * h->ldw * sizeof(double);
+  int64_t cap = std::max<int64_t>(1, (int64_t)((6ull << 30) / per));
+  return (int)std::min(nb, cap);
+}
+
+void build_triple_list(int64_t o, std::vector<int>& out) {
+  out.clear();
+  for (int i = 0; i < o; ++i)
+    for (int j = 0; j <= i; ++j)
+      for (int k = 0; k <= j; ++k) {
+        if (i == j && j == k) continue;
+        out.push_back(i);
+        out.push_back(j);
+        out.push_back(k);
+      }
+}
+
+GemmParams gemm_params(const mpqc_t_handle* h, int nbatch, const int* triples_dev) {
+  GemmParams P;
+  P.v = (int)h->v;
+  P.o = (int)h->o;
+  P.Kp = (int)h->Kp;
+  P.kblocks = h->kblocks;
+  P.tp = h->tp;
+  P.tq = h->tq;
+  P.tn = h->tn;
+  P.nfrag = h->nfrag;
+  P.npt = h->npt;
+  P.nqt = h->nqt;
+  P.nnt = h->nnt;
+  P.tiles_per_group = h->npt * h->nqt * h->nnt;
+  P.total_tiles = nbatch * 3 * P.tiles_per_group;
+  P.ldw = h->ldw;
+  P.rows_valid = h->tp * h->tq;
+  P.triples = triples_dev;
+  P.w = h->W;
+  return P;
+}
+
+int launch_gemm(mpqc_t_handle* h, int nbatch, const int* triples_dev) {
+  GemmParams P = gemm_params(h, nbatch, triples_dev);
+  int grid = std::min(h->num_sms, P.total_tiles);
+  w_contract_dmma_kernel<<<grid, kGemmThreads, kGemmSmemBytes, h->stream>>>(h->tmA_n, h->tmA_t, h->tmB, P);
+  MPQC_T_CUDA(cudaGetLastError());
+  return MPQC_T_OK;
+}
+
+int launch_energy(mpqc_t_handle* h, int nbatch, const int* triples_dev, double* unit_e_dev) {
+  EnergyParams E;
+  E.v = (int)h->v;
+  E.o = (int)h->o;
+  E.ldw = h->ldw;
+  E.ntile = h->ntile;
+  E.ntt = h->ntt;
+  E.triples = triples_dev;
+  E.w = h->W;
+  E.gv = h->GV;
+  E.t1t = h->T1T;
+  E.eps_occ = h->eps_occ;
+  E.eps_vir = h->eps_vir;
+  E.tile_sets = h->tile_sets;
+  E.partial = h->partial;
+  t_energy_fused_kernel<<<dim3((unsigned)h->ntt, (unsigned)nbatch), kEThreads, 0, h->stream>>>(E);
+  MPQC_T_CUDA(cudaGetLastError());
+  t_energy_finish_kernel<<<nbatch, 256, 0, h->stream>>>(h->partial, h->ntt, triples_dev, unit_e_dev);
+  MPQC_T_CUDA(cudaGetLastError());
+  return MPQC_T_OK;
+}
+
+// copy host->device (or alias a device pointer) for the small/medium inputs
+struct Staged {
+  const double* ptr = nullptr;
+  double* owned = nullptr;
+  ~Staged() { cudaFree(owned); }
+};
+
+int stage_in(Staged& s, const double* src, size_t n, bool on_device, cudaStream_t st, int64_t* h2d) {
+  if (on_device) {
+    s.ptr = src;
+    return MPQC_T_OK;
+  }
+  MPQC_T_CUDA(cudaMalloc(&s.owned, std::max<size_t>(n, 1) * sizeof(double)));
+  MPQC_T_CUDA(cudaMemcpyAsync(s.owned, src, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (h2d) *h2d += (int64_t)(n * sizeof(double));
+  s.ptr = s.owned;
+  return MPQC_T_OK;
+}
+
+int upload_impl(mpqc_t_handle* h, const mpqc_t_problem* p, bool on_device, mpqc_t_stats* stats) {
+  const int64_t o = h->o, v = h->v, Kp = h->Kp;
+  cudaStream_t st = h->stream;
+  int64_t launches = 0, h2d = 0;
+  const double t0 = now_s();
+  double t_copy = 0.0;
+
+  MPQC_T_CUDA(cudaMemsetAsync(h->A, 0, (size_t)o * v * v * Kp * sizeof(double), st));
+  MPQC_T_CUDA(cudaMemsetAsync(h->B, 0, (size_t)o * o * v * Kp * sizeof(double), st));
+
+  {
+    double tc = now_s();
+    if (!on_device) {
+      MPQC_T_CUDA(cudaMemcpyAsync(h->eps_occ, p->eps_occ, o * sizeof(double), cudaMemcpyHostToDevice, st));
+      MPQC_T_CUDA(cudaMemcpyAsync(h->eps_vir, p->eps_vir, v * sizeof(double), cudaMemcpyHostToDevice, st));
+      h2d += (o + v) * 8;
+    } else {
+      MPQC_T_CUDA(cudaMemcpyAsync(h->eps_occ, p->eps_occ, o * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      MPQC_T_CUDA(cudaMemcpyAsync(h->eps_vir, p->eps_vir, v * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+    Staged t1, t2, gabij, gaijk;
+    MPQC_T_TRY(stage_in(t1, p->t1, (size_t)v * o, on_device, st, &h2d));
+    MPQC_T_TRY(stage_in(t2, p->t2, (size_t)v * v * o * o, on_device, st, &h2d));
+    MPQC_T_TRY(stage_in(gabij, p->g_abij, (size_t)v * v * o * o, on_device, st, &h2d));
+    MPQC_T_TRY(stage_in(gaijk, p->g_aijk, (size_t)v * o * o * o, on_device, st, &h2d));
+    if (!on_device) {
+      MPQC_T_CUDA(cudaStreamSynchronize(st));
+      t_copy += now_s() - tc;
+    }
+    // T1T[i][a] = t1[a][i]
+    MPQC_T_TRY(launch_transpose(st, t1.ptr, h->T1T, v, 1, o, 1, v, 0, 0, &launches));
+    // GV[(i,j)][(a,b)] = g_abij[(a,b)][(i,j)]
+    MPQC_T_TRY(launch_transpose(st, gabij.ptr, h->GV, v * v, 1, o * o, 1, v * v, 0, 0, &launches));
+    // B particle part: t2[kap][r][(y,z)] -> B[(y,z)][r][kap]
+    MPQC_T_TRY(launch_transpose(st, t2.ptr, h->B, v, v, o * o, 1, v * Kp, 0, Kp, &launches));
+    // B hole part: g_aijk[r][(y,z)][l] -> B[(y,z)][r][v + l]
+    MPQC_T_TRY(launch_copy_hole(st, gaijk.ptr, h->B, v, o * o, o, Kp, v * Kp, v, 1.0, &launches));
+    // A hole part: -t2[(p,q)][x][l] -> A[x][(p,q)][v + l]
+    MPQC_T_TRY(launch_copy_hole(st, t2.ptr, h->A, v * v, o, o, Kp, v * v * Kp, v, -1.0, &launches));
+    MPQC_T_CUDA(cudaStreamSynchronize(st));  // staged buffers are freed on scope exit
+  }
+
+  // A particle part: g_abci[kap][p][(q,x)] -> A[x][p][q][kap], streamed in kap slabs
+  if (on_device) {
+    MPQC_T_TRY(launch_transpose(st, p->g_abci, h->A, v, v, v * o, o, Kp, v * v * Kp, v * Kp, &launches));
+    MPQC_T_CUDA(cudaStreamSynchronize(st));
+  } else {
+    const size_t row = (size_t)v * v * o;  // doubles per kap
+    int64_t slab = std::max<int64_t>(1, std::min<int64_t>(v, (int64_t)((1ull << 30) / (row * 8 + 1)) + 1));
+    double* buf[2] = {nullptr, nullptr};
+    cudaEvent_t done[2];
+    for (int s = 0; s < 2; ++s) {
+      MPQC_T_CUDA(cudaMalloc(&buf[s], (size_t)slab * row * sizeof(double)));
+      MPQC_T_CUDA(cudaEventCreateWithFlags(&done[s], cudaEventDisableTiming));
+    }
+    int which = 0;
+    int rc = MPQC_T_OK;
+    for (int64_t d0 = 0; d0 < v && rc == MPQC_T_OK; d0 += slab, which ^= 1) {
+      int64_t nd = std::min(slab, v - d0);
+      double tc = now_s();
+      cudaEventSynchronize(done[which]);
+      cudaError_t e = cudaMemcpyAsync(buf[which], p->g_abci + (size_t)d0 * row, (size_t)nd * row * sizeof(double),
+                                      cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) { rc = cuda_status(e, "cudaMemcpyAsync(g_abci slab)", __FILE__, __LINE__); break; }
+      t_copy += now_s() - tc;
+      h2d += (int64_t)(nd * row * 8);
+      rc = launch_transpose(st, buf[which], h->A + d0, nd, v, v * o, o, Kp, v * v * Kp, v * Kp, &launches);
+      cudaEventRecord(done[which], st);
+    }
+    cudaStreamSynchronize(st);
+    for (int s = 0; s < 2; ++s) {
+      cudaFree(buf[s]);
+      cudaEventDestroy(done[s]);
+    }
+    MPQC_T_TRY(rc);
+  }
+  MPQC_T_CUDA(cudaGetLastError());
+  h->uploaded = true;
+  if (stats) {
+    double tot = now_s() - t0;
+    stats->seconds_upload += t_copy;
+    stats->seconds_relayout += tot - t_copy;
+    stats->kernel_launches += launches;
+    stats->bytes_h2d += h2d;
+  }
+  return MPQC_T_OK;
+}
+
+// Run an explicit list of units (indices into the global enumeration).  unit_e_host[n] receives the
+// weighted per-unit energies.  Synchronises the stream before returning.
+int run_units(mpqc_t_handle* h, const std::vector<int>& all_triples, const int64_t* units, int64_t n, int batch,
+              double* unit_e_host, mpqc_t_stats* stats, bool profile) {
+  if (n == 0) return MPQC_T_OK;
+  MPQC_T_CUDA(cudaSetDevice(h->device));
+  if (batch <= 0) batch = auto_batch(h);
+  batch = (int)std::min<int64_t>(batch, n);
+  batch = std::min(batch, 65535);
+  MPQC_T_TRY(ensure_work(h, batch));
+  MPQC_T_TRY(ensure_units(h, n));
+  std::vector<int> tri((size_t)n * 3);
+  for (int64_t u = 0; u < n; ++u)
+    for (int c = 0; c < 3; ++c) tri[3 * u + c] = all_triples[3 * units[u] + c];
+  MPQC_T_CUDA(cudaMemcpyAsync(h->triples_dev, tri.data(), tri.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+
+  const int64_t nbatches = (n + batch - 1) / batch;
+  profile = profile && nbatches <= 8192;
+  std::vector<cudaEvent_t> ev;
+  cudaEvent_t e_begin, e_end;
+  MPQC_T_CUDA(cudaEventCreate(&e_begin));
+  MPQC_T_CUDA(cudaEventCreate(&e_end));
+  if (profile) {
+    ev.resize((size_t)nbatches * 3);
+    for (auto& e : ev) MPQC_T_CUDA(cudaEventCreate(&e));
+  }
+  MPQC_T_CUDA(cudaEventRecord(e_begin, h->stream));
+  int64_t launches = 0;
+  for (int64_t bi = 0; bi < nbatches; ++bi) {
+    const int64_t off = bi * batch;
+    const int nb = (int)std::min<int64_t>(batch, n - off);
+    if (profile) cudaEventRecord(ev[3 * bi], h->stream);
+    MPQC_T_TRY(launch_gemm(h, nb, h->triples_dev + 3 * off));
+    if (profile) cudaEventRecord(ev[3 * bi + 1], h->stream);
+    MPQC_T_TRY(launch_energy(h, nb, h->triples_dev + 3 * off, h->unit_e_dev + off));
+    if (profile) cudaEventRecord(ev[3 * bi + 2], h->stream);
+    launches += 3;
+  }
+  MPQC_T_CUDA(cudaEventRecord(e_end, h->stream));
+  MPQC_T_CUDA(cudaMemcpyAsync(unit_e_host, h->unit_e_dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  MPQC_T_CUDA(cudaStreamSynchronize(h->stream));
+  MPQC_T_CUDA(cudaGetLastError());
+  if (stats) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e_begin, e_end);
+    stats->seconds_compute += ms * 1e-3;
+    if (profile) {
+      double tg = 0, te = 0;
+      for (int64_t bi = 0; bi < nbatches; ++bi) {
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, ev[3 * bi], ev[3 * bi + 1]);
+        cudaEventElapsedTime(&b, ev[3 * bi + 1], ev[3 * bi + 2]);
+        tg += a * 1e-3;
+        te += b * 1e-3;
+      }
+      stats->seconds_contract += tg;
+      stats->seconds_energy += te;
+    }
+    stats->units += n;
+    stats->kernel_launches += launches;
+    stats->flops += (double)n * mpqc_t_unit_flops(h->o, h->v);
+    double mpad = (double)h->npt * h->nqt * kBM, npad = (double)h->nnt * h->tn;
+    stats->flops_executed += (double)n * 3.0 * 2.0 * 2.0 * mpad * npad * (double)h->Kp;
+    stats->bytes_d2h += n * 8;
+    stats->bytes_h2d += n * 12;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  cudaEventDestroy(e_begin);
+  cudaEventDestroy(e_end);
+  return MPQC_T_OK;
+}
+
+int validate_problem(const mpqc_t_problem* p) {
+  MPQC_T_CHECK(p != nullptr, MPQC_T_ERR_BAD_ARG, "problem is NULL");
+  MPQC_T_CHECK(p->o >= 1 && p->v >= 1, MPQC_T_ERR_BAD_ARG, "o and v must be >= 1");
+  MPQC_T_CHECK(p->o <= 4096 && p->v <= 2040, MPQC_T_ERR_BAD_ARG, "o <= 4096 and v <= 2040 supported");
+  MPQC_T_CHECK(p->eps_occ && p->eps_vir && p->t1 && p->t2 && p->g_abij && p->g_aijk && p->g_abci,
+               MPQC_T_ERR_BAD_ARG, "a tensor pointer is NULL");
+  return MPQC_T_OK;
+}
+
+}  // namespace
+
+// -------------------------------------------------------------------------------------------------
+// C ABI
+// -------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* mpqc_t_version(void) { return "mpqc_t_cuda 0.1 (sm_100a, abi 1)"; }
+
+const char* mpqc_t_strerror(int status) {
+  switch (status) {
+    case MPQC_T_OK: return "ok";
+    case MPQC_T_ERR_BAD_ARG: return "bad argument";
+    case MPQC_T_ERR_NO_DEVICE: return "no usable CUDA device (there is no CPU fallback)";
+    case MPQC_T_ERR_OOM: return "out of device memory";
+    case MPQC_T_ERR_CUDA: return "CUDA runtime/driver error";
+    case MPQC_T_ERR_NCCL: return "NCCL error";
+    case MPQC_T_ERR_INTERNAL: return "internal error";
+    default: return "unknown status";
+  }
+}
+
+const char* mpqc_t_last_error(void) { return last_error_string().c_str(); }
+
+int64_t mpqc_t_triple_count(int64_t o) {
+  if (o < 1) return 0;
+  return o * (o + 1) * (o + 2) / 6 - o;
+}
+
+int mpqc_t_triple_of_unit(int64_t o, int64_t unit, int32_t* i, int32_t* j, int32_t* k) {
+  MPQC_T_CHECK(i && j && k, MPQC_T_ERR_BAD_ARG, "NULL output");
+  MPQC_T_CHECK(unit >= 0 && unit < mpqc_t_triple_count(o), MPQC_T_ERR_BAD_ARG, "unit out of range");
+  int64_t u = 0;
+  for (int64_t a = 0; a < o; ++a) {
+    // units with first index a: (a+1)(a+2)/2 - 1
+    int64_t na = (a + 1) * (a + 2) / 2 - 1;
+    if (unit < u + na) {
+      int64_t r = unit - u;
+      for (int64_t b = 0; b <= a; ++b) {
+        int64_t nb = (b + 1) - ((b == a) ? 1 : 0);
+        if (r < nb) {
+          *i = (int32_t)a;
+          *j = (int32_t)b;
+          *k = (int32_t)r;
+          return MPQC_T_OK;
+        }
+        r -= nb;
+      }
+    }
+    u += na;
+  }
+  return fail(MPQC_T_ERR_INTERNAL, "triple enumeration", __FILE__, __LINE__);
+}
+
+double mpqc_t_flops(int64_t o, int64_t v) { return 2.0 * (double)o * o * o * (double)v * v * v * (double)(v + o); }
+double mpqc_t_unit_flops(int64_t o, int64_t v) { return 12.0 * (double)v * v * v * (double)(v + o); }
+
+int mpqc_t_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int mpqc_t_create(mpqc_t_handle** out, int64_t o, int64_t v, int32_t device) {
+  MPQC_T_CHECK(out != nullptr, MPQC_T_ERR_BAD_ARG, "handle pointer is NULL");
+  *out = nullptr;
+  MPQC_T_CHECK(o >= 1 && v >= 1 && o <= 4096 && v <= 2040, MPQC_T_ERR_BAD_ARG, "need 1 <= o <= 4096, 1 <= v <= 2040");
+  int ndev = mpqc_t_device_count();
+  MPQC_T_CHECK(ndev > 0, MPQC_T_ERR_NO_DEVICE, "no CUDA device visible; the (T) path has no CPU fallback");
+  MPQC_T_CHECK(device >= 0 && device < ndev, MPQC_T_ERR_BAD_ARG, "device ordinal out of range");
+  MPQC_T_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  MPQC_T_CUDA(cudaGetDeviceProperties(&prop, device));
+  MPQC_T_CHECK(prop.major >= 10, MPQC_T_ERR_NO_DEVICE, "device is not sm_100-class (kernels are sm_100a only)");
+  mpqc_t_handle* h = new (std::nothrow) mpqc_t_handle();
+  MPQC_T_CHECK(h != nullptr, MPQC_T_ERR_OOM, "host allocation failed");
+  h->device = device;
+  h->o = o;
+  h->v = v;
+  h->Kp = std::max<int64_t>(16, roundup(v + o, 8));
+  h->num_sms = prop.multiProcessorCount;
+  int rc = [&]() -> int {
+    MPQC_T_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    MPQC_T_CUDA(cudaMalloc(&h->A, (size_t)o * v * v * h->Kp * sizeof(double)));
+    MPQC_T_CUDA(cudaMalloc(&h->B, (size_t)o * o * v * h->Kp * sizeof(double)));
+    MPQC_T_CUDA(cudaMalloc(&h->GV, (size_t)o * o * v * v * sizeof(double)));
+    MPQC_T_CUDA(cudaMalloc(&h->T1T, (size_t)o * v * sizeof(double)));
+    MPQC_T_CUDA(cudaMalloc(&h->eps_occ, (size_t)o * sizeof(double)));
+    MPQC_T_CUDA(cudaMalloc(&h->eps_vir, (size_t)v * sizeof(double)));
+    MPQC_T_TRY(plan(h));
+    MPQC_T_TRY(make_maps(h));
+    std::vector<uint8_t> sets((size_t)h->ntt * 4);
+    size_t n = 0;
+    for (int a = 0; a < h->ntile; ++a)
+      for (int b = 0; b <= a; ++b)
+        for (int c = 0; c <= b; ++c) {
+          sets[n++] = (uint8_t)a;
+          sets[n++] = (uint8_t)b;
+          sets[n++] = (uint8_t)c;
+          sets[n++] = 0;
+        }
+    MPQC_T_CUDA(cudaMalloc(&h->tile_sets, sets.size()));
+    MPQC_T_CUDA(cudaMemcpy(h->tile_sets, sets.data(), sets.size(), cudaMemcpyHostToDevice));
+    MPQC_T_CUDA(cudaFuncSetAttribute(w_contract_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kGemmSmemBytes));
+    return MPQC_T_OK;
+  }();
+  if (rc != MPQC_T_OK) {
+    std::string keep = last_error_string();
+    mpqc_t_destroy(h);
+    last_error_string() = keep;
+    return rc;
+  }
+  *out = h;
+  return MPQC_T_OK;
+}
+
+int mpqc_t_destroy(mpqc_t_handle* h) {
+  if (!h) return MPQC_T_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  free_work(h);
+  cudaFree(h->A);
+  cudaFree(h->B);
+  cudaFree(h->GV);
+  cudaFree(h->T1T);
+  cudaFree(h->eps_occ);
+  cudaFree(h->eps_vir);
+  cudaFree(h->tile_sets);
+  cudaFree(h->triples_dev);
+  cudaFree(h->unit_e_dev);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  cudaGetLastError();
+  delete h;
+  return MPQC_T_OK;
+}
+
+void* mpqc_t_stream(mpqc_t_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int mpqc_t_upload(mpqc_t_handle* h, const mpqc_t_problem* p, int32_t on_device, mpqc_t_stats* stats) {
+  MPQC_T_CHECK(h != nullptr, MPQC_T_ERR_BAD_ARG, "handle is NULL");
+  MPQC_T_TRY(validate_problem(p));
+  MPQC_T_CHECK(p->o == h->o && p->v == h->v, MPQC_T_ERR_BAD_ARG, "problem dimensions differ from the handle's");
+  MPQC_T_CUDA(cudaSetDevice(h->device));
+  return upload_impl(h, p, on_device != 0, stats);
+}
+
+int mpqc_t_run(mpqc_t_handle* h, int64_t first, int64_t stride, int64_t count, int32_t batch, double* partial_e,
+               double* unit_e, mpqc_t_stats* stats) {
+  MPQC_T_CHECK(h != nullptr && partial_e != nullptr, MPQC_T_ERR_BAD_ARG, "handle or output is NULL");
+  MPQC_T_CHECK(h->uploaded, MPQC_T_ERR_BAD_ARG, "mpqc_t_upload has not been called on this handle");
+  if (stride <= 0) stride = 1;
+  const int64_t nt = mpqc_t_triple_count(h->o);
+  MPQC_T_CHECK(first >= 0, MPQC_T_ERR_BAD_ARG, "unit_first < 0");
+  int64_t avail = first < nt ? (nt - first + stride - 1) / stride : 0;
+  if (count < 0 || count > avail) count = avail;
+  *partial_e = 0.0;
+  const double t0 = now_s();
+  if (count > 0) {
+    std::vector<int> all;
+    build_triple_list(h->o, all);
+    std::vector<int64_t> units((size_t)count);
+    for (int64_t u = 0; u < count; ++u) units[u] = first + u * stride;
+    std::vector<double> ue((size_t)count);
+    MPQC_T_TRY(run_units(h, all, units.data(), count, batch, ue.data(), stats, getenv("MPQC_T_PROFILE") != nullptr));
+    double s = 0.0;
+    for (int64_t u = 0; u < count; ++u) s += ue[u];   // fixed unit order -> deterministic
+    *partial_e = s;
+    if (unit_e) memcpy(unit_e, ue.data(), (size_t)count * sizeof(double));
+  }
+  if (stats) {
+    stats->seconds_total += now_s() - t0;
+    stats->ngpu = 1;
+  }
+  return MPQC_T_OK;
+}
+
+int mpqc_t_debug_w(mpqc_t_handle* h, int32_t i, int32_t j, int32_t k, double* w_host) {
+  MPQC_T_CHECK(h && w_host, MPQC_T_ERR_BAD_ARG, "NULL argument");
+  MPQC_T_CHECK(h->uploaded, MPQC_T_ERR_BAD_ARG, "mpqc_t_upload has not been called on this handle");
+  MPQC_T_CHECK(i >= 0 && j >= 0 && k >= 0 && i < h->o && j < h->o && k < h->o, MPQC_T_ERR_BAD_ARG, "triple out of range");
+  MPQC_T_CUDA(cudaSetDevice(h->device));
+  MPQC_T_TRY(ensure_work(h, 1));
+  MPQC_T_TRY(ensure_units(h, 1));
+  int tri[3] = {i, j, k};
+  MPQC_T_CUDA(cudaMemcpyAsync(h->triples_dev, tri, sizeof(tri), cudaMemcpyHostToDevice, h->stream));
+  MPQC_T_TRY(launch_gemm(h, 1, h->triples_dev));
+  const int64_t v = h->v, ldw = h->ldw;
+  std::vector<double> n((size_t)3 * v * v * ldw);
+  MPQC_T_CUDA(cudaMemcpyAsync(n.data(), h->W, n.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  MPQC_T_CUDA(cudaStreamSynchronize(h->stream));
+  const double* n0 = n.data();
+  const double* n1 = n0 + v * v * ldw;
+  const double* n2 = n1 + v * v * ldw;
+  for (int64_t a = 0; a < v; ++a)
+    for (int64_t b = 0; b < v; ++b)
+      for (int64_t c = 0; c < v; ++c)
+        w_host[(a * v + b) * v + c] = n0[(a * v + b) * ldw + c] + n1[(a * v + c) * ldw + b] + n2[(c * v + b) * ldw + a];
+  return MPQC_T_OK;
+}
+
+int mpqc_t_energy(const mpqc_t_problem* p, const mpqc_t_options* opt_in, double* e_t, mpqc_t_stats* stats_out) {
+  MPQC_T_CHECK(e_t != nullptr, MPQC_T_ERR_BAD_ARG, "e_t is NULL");
+  MPQC_T_TRY(validate_problem(p));
+  mpqc_t_options opt;
+  memset(&opt, 0, sizeof(opt));
+  if (opt_in) opt = *opt_in;
+  const int ngpu = opt.ngpu > 0 ? opt.ngpu : 1;
+  MPQC_T_CHECK(!(opt.inputs_on_device && ngpu != 1), MPQC_T_ERR_BAD_ARG, "inputs_on_device requires ngpu == 1");
+  const int ndev = mpqc_t_device_count();
+  MPQC_T_CHECK(ndev > 0, MPQC_T_ERR_NO_DEVICE, "no CUDA device visible; the (T) path has no CPU fallback");
+  std::vector<int> devs(ngpu);
+  for (int g = 0; g < ngpu; ++g) {
+    devs[g] = opt.device_ids ? opt.device_ids[g] : g;
+    MPQC_T_CHECK(devs[g] >= 0 && devs[g] < ndev, MPQC_T_ERR_BAD_ARG, "device ordinal out of range");
+  }
+  const double t0 = now_s();
+  mpqc_t_stats stats;
+  memset(&stats, 0, sizeof(stats));
+
+  // this process' shard of the unit list
+  const int64_t nt = mpqc_t_triple_count(p->o);
+  int64_t stride = opt.unit_stride > 0 ? opt.unit_stride : 1;
+  MPQC_T_CHECK(opt.unit_first >= 0, MPQC_T_ERR_BAD_ARG, "unit_first < 0");
+  int64_t avail = opt.unit_first < nt ? (nt - opt.unit_first + stride - 1) / stride : 0;
+  int64_t count = (opt.unit_count < 0 || opt.unit_count > avail) ? avail : opt.unit_count;
+  std::vector<int64_t> units((size_t)count);
+  for (int64_t u = 0; u < count; ++u) units[u] = opt.unit_first + u * stride;
+  std::vector<double> unit_e((size_t)count, 0.0);
+  std::vector<int> all;
+  build_triple_list(p->o, all);
+
+  // static share first (unit u -> gpu u % ngpu for the first ~7/8), then a shared work-stealing tail
+  std::vector<mpqc_t_stats> gstats(ngpu);
+  std::vector<int> rcs(ngpu, MPQC_T_OK);
+  std::vector<std::string> msgs(ngpu);
+  std::atomic<int64_t> tail_next;
+  const int64_t static_n = ngpu > 1 ? (count / 8) * 7 / ngpu * ngpu : count;
+  tail_next.store(static_n);
+  const bool profile = getenv("MPQC_T_PROFILE") != nullptr;
+
+  auto worker = [&](int g) {
+    mpqc_t_stats& gs = gstats[g];
+    memset(&gs, 0, sizeof(gs));
+    mpqc_t_handle* h = nullptr;
+    int rc = mpqc_t_create(&h, p->o, p->v, devs[g]);
+    if (rc == MPQC_T_OK) rc = mpqc_t_upload(h, p, opt.inputs_on_device, &gs);
+    if (rc == MPQC_T_OK) {
+      // static part
+      std::vector<int64_t> mine;
+      for (int64_t u = g; u < static_n; u += ngpu) mine.push_back(u);
+      std::vector<int64_t> idx(mine.size());
+      std::vector<double> e(mine.size());
+      for (size_t q = 0; q < mine.size(); ++q) idx[q] = units[mine[q]];
+      rc = run_units(h, all, idx.data(), (int64_t)idx.size(), opt.batch, e.data(), &gs, profile);
+      if (rc == MPQC_T_OK)
+        for (size_t q = 0; q < mine.size(); ++q) unit_e[mine[q]] = e[q];
+      // work-stealing tail
+      int64_t chunk = opt.steal_chunk > 0 ? opt.steal_chunk : std::max<int64_t>(1, auto_batch(h)) * 4;
+      while (rc == MPQC_T_OK) {
+        int64_t s = tail_next.fetch_add(chunk);
+        if (s >= count) break;
+        int64_t n = std::min(chunk, count - s);
+        std::vector<double> e2((size_t)n);
+        rc = run_units(h, all, units.data() + s, n, opt.batch, e2.data(), &gs, profile);
+        if (rc == MPQC_T_OK)
+          for (int64_t q = 0; q < n; ++q) unit_e[s + q] = e2[q];
+      }
+    }
+    if (rc != MPQC_T_OK) msgs[g] = last_error_string();
+    mpqc_t_destroy(h);
+    rcs[g] = rc;
+  };
+
+  if (ngpu == 1) {
+    worker(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int g = 0; g < ngpu; ++g) th.emplace_back(worker, g);
+    for (auto& t : th) t.join();   // joined before returning (SURVEY 8b threading contract)
+  }
+  for (int g = 0; g < ngpu; ++g)
+    if (rcs[g] != MPQC_T_OK) {
+      last_error_string() = msgs[g];
+      return rcs[g];
+    }
+  double e = 0.0;
+  for (int64_t u = 0; u < count; ++u) e += unit_e[u];
+  *e_t = e;
+
+  for (int g = 0; g < ngpu; ++g) {
+    stats.seconds_upload = std::max(stats.seconds_upload, gstats[g].seconds_upload);
+    stats.seconds_relayout = std::max(stats.seconds_relayout, gstats[g].seconds_relayout);
+    stats.seconds_compute = std::max(stats.seconds_compute, gstats[g].seconds_compute);
+    stats.seconds_contract = std::max(stats.seconds_contract, gstats[g].seconds_contract);
+    stats.seconds_energy = std::max(stats.seconds_energy, gstats[g].seconds_energy);
+    stats.flops += gstats[g].flops;
+    stats.flops_executed += gstats[g].flops_executed;
+    stats.units += gstats[g].units;
+    stats.kernel_launches += gstats[g].kernel_launches;
+    stats.bytes_h2d += gstats[g].bytes_h2d;
+    stats.bytes_d2h += gstats[g].bytes_d2h;
+  }
+  stats.ngpu = ngpu;
+  stats.seconds_total = now_s() - t0;
+  if (opt.verbose) {
+    // same line the reference prints, ccsd_t.h:175
+    printf("(T) Energy: %.15g Time: %g S\n", e, stats.seconds_total);
+    fflush(stdout);
+  }
+  if (stats_out) *stats_out = stats;
+  return MPQC_T_OK;
+}
+
+int mpqc_t_microbench(int32_t device, int32_t which, double* tflops) {
+  MPQC_T_CHECK(tflops != nullptr, MPQC_T_ERR_BAD_ARG, "tflops is NULL");
+  int ndev = mpqc_t_device_count();
+  MPQC_T_CHECK(ndev > 0, MPQC_T_ERR_NO_DEVICE, "no CUDA device visible");
+  MPQC_T_CHECK(device >= 0 && device < ndev, MPQC_T_ERR_BAD_ARG, "device ordinal out of range");
+  MPQC_T_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  MPQC_T_CUDA(cudaGetDeviceProperties(&prop, device));
+  double* out = nullptr;
+  MPQC_T_CUDA(cudaMalloc(&out, 64));
+  const int blocks = prop.multiProcessorCount * 4, threads = 256, iters = 20000;
+  cudaEvent_t e0, e1;
+  MPQC_T_CUDA(cudaEventCreate(&e0));
+  MPQC_T_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0);
+    if (which == 0) microbench_dmma_kernel<<<blocks, threads>>>(out, iters);
+    else microbench_dfma_kernel<<<blocks, threads>>>(out, iters);
+    cudaEventRecord(e1);
+    MPQC_T_CUDA(cudaEventSynchronize(e1));
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0) best = std::min(best, ms);
+  }
+  MPQC_T_CUDA(cudaGetLastError());
+  double fl;
+  if (which == 0) fl = (double)blocks * (threads / 32) * (double)iters * 8.0 * 512.0;
+  else fl = (double)blocks * threads * (double)iters * 8.0 * 2.0;
+  *tflops = fl / (best * 1e-3) * 1e-12;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  return MPQC_T_OK;
+}
+
+}  // extern "C"
