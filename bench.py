@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- (T) throughput of the B200 path on the uracil-trimer/6-31G* shaped workload.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (N>1: launched by torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port of the reference's
+                                                             # default 'coarse' (T) on the box's host cores
+
+A "step" is one pass of the hot path over one batch of `--units` occupied triples (i>=j>=k) per GPU of the
+synthetic o=63, v=297 problem (BASELINE.json configs[3], the config the metric is quoted on; it fits one
+GPU).  metric = FP64 TFLOP/s with the algorithmic work model 12 v^3 (v+o) FLOPs per triple
+(= 2 o^3 v^3 (v+o) for the whole job).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (o, v, description)
+    "uracil-trimer-6-31Gs": (63, 297, "uracil trimer CCSD(T)/6-31G* shape"),
+    "uracil-dimer-6-31Gs": (42, 198, "uracil dimer CCSD(T)/6-31G* shape"),
+    "benzene-cc-pVDZ": (21, 93, "benzene CCSD(T)/cc-pVDZ shape"),
+    "water10-cc-pVTZ": (40, 530, "(H2O)10 CCSD(T)/cc-pVTZ shape"),
+    "synthetic-o50-v500": (50, 500, "synthetic random T2/integrals"),
+}
+FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 * 1e-12     # 148 SMs x 64 DFMA/clk x 1.965 GHz = 37.2
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="uracil-trimer-6-31Gs", choices=sorted(WORKLOADS))
+    ap.add_argument("--units", type=int, default=74, help="occupied triples per GPU per step")
+    ap.add_argument("--e2e-units", type=int, default=2048, help="triples per GPU in the end-to-end (host buffer) call")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-blocks", type=int, default=2, help="(a,b,c) virtual-block triples in the CPU sample")
+    return ap.parse_args()
+
+
+# -------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, val in zip(names, r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+        pw = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+def cpu_sample(host: dict, o: int, v: int, nblocks: int, vir_block: int = 8):
+    """Time the oracle port of the reference's default coarse (T) (ccsd_t.h:443-640) on a bounded sample of
+    strictly ordered (a>b>c) virtual-block triples; all host threads via numpy/OpenBLAS matmul."""
+    from oracle import ccsd_t_oracle as oc
+    nb = (v + vir_block - 1) // vir_block
+    # global_iter numbering of the a>=b>=c loop; pick strictly ordered full-size blocks spread over the range
+    picks, it = [], 0
+    want = set()
+    for a in range(nb):
+        for b in range(a + 1):
+            for c in range(b + 1):
+                it += 1
+                if a > b > c and a < nb - 1:
+                    picks.append(it)
+    if not picks:
+        picks = list(range(1, it + 1))
+    stride = max(1, len(picks) // nblocks)
+    want = set(picks[::stride][:nblocks])
+    args = (host["t1"], host["t2"], host["g_abij"], host["g_aijk"], host["g_abci"], host["eps_occ"], host["eps_vir"])
+    t0 = time.perf_counter()
+    oc.coarse(*args, vir_block=vir_block, block_filter=want)
+    dt = time.perf_counter() - t0
+    fl = len(want) * 12.0 * vir_block ** 3 * float(o) ** 3 * (v + o)
+    return fl / dt * 1e-12, dt, len(want)
+
+
+def to_host(pd: dict, pin: bool):
+    import torch
+    out = {}
+    for k, a in pd.items():
+        if torch.is_tensor(a):
+            if pin:
+                h = torch.empty(a.shape, dtype=a.dtype, pin_memory=True)
+                h.copy_(a)
+                out[k] = h
+            else:
+                out[k] = a.cpu()
+        else:
+            out[k] = a
+    return out
+
+
+def as_numpy(hd: dict):
+    import torch
+    return {k: (a.numpy() if torch.is_tensor(a) else a) for k, a in hd.items()}
+
+
+# -------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU arm: the reference's own algorithm for this path (oracle port; the reference binary cannot be built
+    here) on the host cores.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    o, v, desc = WORKLOADS[args.workload]
+    if torch.cuda.is_available():
+        from mpqc_b200.synthetic import make_problem_torch
+        pd = make_problem_torch(o, v, "cuda")
+        host = as_numpy(to_host(pd, pin=False))
+        del pd
+        torch.cuda.empty_cache()
+    else:
+        from mpqc_b200.synthetic import make_problem
+        host = make_problem(o, v)
+    cores = os.cpu_count()
+    for _ in range(args.warmup):
+        cpu_sample(host, o, v, 1)
+    t0 = time.perf_counter()
+    tf_sum, n = 0.0, 0
+    fl_total = 0.0
+    for _ in range(args.steps):
+        tf, dt, nblk = cpu_sample(host, o, v, 1)
+        fl_total += tf * dt
+        n += 1
+    wall = time.perf_counter() - t0
+    value = fl_total / wall
+    line = {
+        "impl": "reference", "metric": "(T) FP64 TFLOP/s (algorithmic 2 o^3 v^3 (v+o) work model)", "value": value,
+        "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": wall / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: o={o}, v={v} ({desc})",
+                   "step": "one strictly ordered (a>b>c) virtual-block triple (block 8) of the reference's coarse loop"},
+        "cpu_baseline": {"value": value, "unit": "TFLOP/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps x 1 (a>b>c) block triple (vir block 8) of ccsd_t.h:443-640, "
+                                   "numpy/OpenBLAS matmul, all host threads"},
+        "e2e": {"value": value, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# -------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mpqc_b200 import lib as L
+    from mpqc_b200.synthetic import make_problem_torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the (T) path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.gpus != world and rank == 0 and world > 1:
+        print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+    n_gpus = world
+
+    lib = L.load()
+    o, v, desc = WORKLOADS[args.workload]
+    pd = make_problem_torch(o, v, f"cuda:{local}")          # same seed on every rank: replicated inputs
+    torch.cuda.synchronize()
+    prob = L.make_problem(o, v, pd["eps_occ"], pd["eps_vir"], pd["t1"], pd["t2"], pd["g_abij"], pd["g_aijk"], pd["g_abci"])
+    h = C.c_void_p()
+    L.check(lib.mpqc_t_create(C.byref(h), o, v, local), "mpqc_t_create")
+    up = L.Stats()
+    L.check(lib.mpqc_t_upload(h, C.byref(prob), 1, C.byref(up)), "mpqc_t_upload")
+    nt = lib.mpqc_t_triple_count(o)
+    unit_flops = lib.mpqc_t_unit_flops(o, v)
+    U = max(1, min(args.units, nt // max(1, n_gpus)))
+    stream = torch.cuda.ExternalStream(lib.mpqc_t_stream(h), device=f"cuda:{local}")
+    os.environ["MPQC_T_PROFILE"] = "1"                      # per-kernel CUDA-event split inside the library
+
+    e_acc = torch.zeros(1, dtype=torch.float64, device=f"cuda:{local}")
+
+    def step(s, st):
+        first = ((s * n_gpus * U) + rank) % max(1, nt - n_gpus * U)
+        e = C.c_double()
+        L.check(lib.mpqc_t_run(h, first, n_gpus, U, 0, C.byref(e), None, C.byref(st)), "mpqc_t_run")
+        if world > 1:
+            t = torch.tensor([e.value], dtype=torch.float64, device=f"cuda:{local}")
+            dist.all_reduce(t)                               # the path's one collective (gop.sum, ccsd_t.h:692)
+            e_acc.add_(t)
+        return e.value
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    dummy = L.Stats()
+    for s in range(args.warmup):
+        step(s, dummy)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    st = L.Stats()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record(stream)
+    for s in range(args.steps):
+        step(args.warmup + s, st)
+    ev1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    dev_s = ev0.elapsed_time(ev1) * 1e-3
+    times = torch.tensor([dev_s, wall, st.seconds_contract, st.seconds_energy], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_s, wall, t_contract, t_energy = (float(x) for x in times.cpu())
+    total_units = args.steps * U * n_gpus
+    value = total_units * unit_flops / dev_s * 1e-12
+
+    # ---- roofline of the dominant kernel (W contraction, FP64 tensor pipe) -----------------------------------
+    tf_peak = C.c_double()
+    L.check(lib.mpqc_t_microbench(local, 0, C.byref(tf_peak)), "microbench")
+    n_gemm_launches = st.kernel_launches // 3
+    per_launch_flops = st.flops / max(1, n_gemm_launches)
+    achieved = st.flops / max(t_contract, 1e-12) * 1e-12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.workload, {}).get("w_contract_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"kernel": "w_contract_dmma_kernel", "bound": "tensor", "achieved": achieved, "peak": tf_peak.value,
+                "unit": "TFLOP/s", "frac": achieved / tf_peak.value, "traffic": traffic,
+                "peak_source": "FP64 tensor peak is not in MEASURED_PEAKS.json; measured live with the DMMA.8x8x4 "
+                               "issue-rate microbenchmark (mpqc_t_microbench); nominal 148 SM x 64 FMA/clk x 1.965 GHz "
+                               f"= {FP64_NOMINAL_TFLOPS:.1f}",
+                "flops_per_launch": per_launch_flops, "launch_ms": t_contract / max(1, n_gemm_launches) * 1e3,
+                "share_of_step": t_contract / max(1e-12, st.seconds_compute)}
+    hbm_peak = None
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        hbm_src = "MEASURED_PEAKS.json"
+    except Exception:
+        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    e_bytes = st.units * 3.0 * 8.0 * v ** 3
+    roofline_energy = {"kernel": "t_energy_fused_kernel", "bound": "hbm", "achieved": e_bytes / max(t_energy, 1e-12) * 1e-9,
+                       "peak": hbm_peak, "unit": "GB/s", "frac": e_bytes / max(t_energy, 1e-12) * 1e-9 / hbm_peak,
+                       "peak_source": hbm_src, "share_of_step": t_energy / max(1e-12, st.seconds_compute)}
+
+    # ---- end to end through the reference-facing call with HOST buffers ---------------------------------------
+    e2e = None
+    host = None
+    if not args.no_e2e:
+        host = to_host(pd, pin=True)
+        hp = L.make_problem(o, v, host["eps_occ"], host["eps_vir"], host["t1"], host["t2"], host["g_abij"],
+                            host["g_aijk"], host["g_abci"])
+        EU = max(1, min(args.e2e_units, nt // n_gpus))
+        opt = L.Options()
+        opt.ngpu = 1
+        dev_ids = (C.c_int32 * 1)(local)
+        opt.device_ids = dev_ids
+        opt.unit_first, opt.unit_stride, opt.unit_count = rank, n_gpus, EU
+        lib.mpqc_t_destroy(h)                               # free the resident copy: the e2e call owns its memory
+        h = None
+        del pd
+        torch.cuda.empty_cache()
+        barrier()
+        est = L.Stats()
+        e = C.c_double()
+        t0 = time.perf_counter()
+        L.check(lib.mpqc_t_energy(C.byref(hp), C.byref(opt), C.byref(e), C.byref(est)), "mpqc_t_energy")
+        if world > 1:
+            t = torch.tensor([e.value], dtype=torch.float64, device=f"cuda:{local}")
+            dist.all_reduce(t)
+        torch.cuda.synchronize()
+        ewall = time.perf_counter() - t0
+        tt = torch.tensor([ewall], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ewall = float(tt.cpu()[0])
+        esteps = EU / U
+        e2e = {"value": EU * n_gpus * unit_flops / ewall * 1e-12, "unit": "TFLOP/s",
+               "h2d_bytes_per_step": est.bytes_h2d / esteps, "d2h_bytes_per_step": est.bytes_d2h / esteps,
+               "units_per_gpu": EU, "seconds": ewall, "seconds_upload": est.seconds_upload,
+               "seconds_relayout": est.seconds_relayout, "seconds_compute": est.seconds_compute,
+               "call": "mpqc_t_energy(host buffers) = H2D of all inputs + relayout + triples + D2H of unit energies"}
+
+    # ---- CPU baseline on rank 0 at N=1 ---------------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        if host is None:
+            host = to_host(pd, pin=False)
+        tf, dt, nblk = cpu_sample(as_numpy(host), o, v, args.cpu_blocks)
+        cpu = {"value": tf, "unit": "TFLOP/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"{nblk} strictly ordered (a>b>c) virtual-block triples (block 8) of the reference's coarse loop "
+                         f"(ccsd_t.h:443-640) on the same o={o}, v={v} inputs, numpy/OpenBLAS, {dt:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": "(T) FP64 TFLOP/s (algorithmic 2 o^3 v^3 (v+o) work model)", "value": value, "unit": "TFLOP/s",
+            "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: o={o}, v={v} ({desc})", "units_per_gpu_per_step": U,
+                       "unit": "one occupied triple i>=j>=k = 12 v^3 (v+o) FLOPs", "parallelism": f"triple-sharded x{n_gpus}",
+                       "l2": "inputs larger than L2 (A operand panels %.1f GB; every step walks different triples)"
+                             % (o * v * v * (v + o) * 8 / 1e9),
+                       "projected_full_job_s": lib.mpqc_t_triple_count(o) * unit_flops / (value * 1e12)},
+            "pct_fp64_tensor_peak": 100.0 * value / n_gpus / tf_peak.value,
+            "wall_ms_per_step": wall / args.steps * 1e3,
+            "roofline": roofline, "roofline_energy": roofline_energy, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(st.kernel_launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if h is not None:
+        lib.mpqc_t_destroy(h)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -19,14 +19,24 @@ import numpy as np
 SEED = 20261017
 
 
+def calibrated_scale(o: int, v: int, target: float = 0.3) -> float:
+    """ERI scale that lands |E(T)| of the synthetic problem near ``target`` Eh (within ~10x), so the
+    1e-9 Eh absolute parity tolerance is a ~1e-9 relative one.  E(T) grows like scale^4; the
+    size dependence E(1) ~ 38 (o^3 v^3 / 3.3e4)^0.75 is an empirical fit over o=4..63, v=8..297."""
+    e1 = 38.0 * (float(o) ** 3 * float(v) ** 3 / 3.3e4) ** 0.75
+    return float((target / e1) ** 0.25)
+
+
 def _eps(rng, o, v):
     eps_occ = np.sort(rng.uniform(-1.5, -0.3, size=o))
     eps_vir = np.sort(rng.uniform(0.2, 3.0, size=v))
     return eps_occ, eps_vir
 
 
-def make_problem(o: int, v: int, seed: int = SEED, scale: float = 1.0, naux: int | None = None):
+def make_problem(o: int, v: int, seed: int = SEED, scale: float | None = None, naux: int | None = None):
     """Return dict of numpy float64 arrays in the reference layouts."""
+    if scale is None:
+        scale = calibrated_scale(o, v)
     rng = np.random.default_rng(seed)
     naux = naux or 2 * (o + v)
     eps_occ, eps_vir = _eps(rng, o, v)
@@ -49,11 +59,13 @@ def make_problem(o: int, v: int, seed: int = SEED, scale: float = 1.0, naux: int
                 g_abci=np.ascontiguousarray(g_abci))
 
 
-def make_problem_torch(o: int, v: int, device, seed: int = SEED, scale: float = 1.0,
+def make_problem_torch(o: int, v: int, device, seed: int = SEED, scale: float | None = None,
                        naux: int | None = None):
     """Same construction on a CUDA device with torch (plumbing: used only to put synthetic
     inputs into HBM for bench.py / large-size tests; not bit-identical to the numpy version)."""
     import torch
+    if scale is None:
+        scale = calibrated_scale(o, v)
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     f64 = torch.float64

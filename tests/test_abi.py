@@ -1,0 +1,98 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/mpqc_t.h declares, fails loudly (no CPU fallback) without a GPU, and its host-only helpers
+agree with the oracle's unit enumeration."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from mpqc_b200 import build as B
+from mpqc_b200 import lib as L
+from oracle import ccsd_t_oracle as oc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HAS_GPU = torch.cuda.is_available()
+
+
+@pytest.fixture(scope="module")
+def lib():
+    B.build()
+    return L.load()
+
+
+def test_header_symbols_are_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "mpqc_t.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(mpqc_t_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(L.SYMBOLS), declared ^ set(L.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_struct_sizes_match_header():
+    # plain-C layout: 2 int64 + 7 pointers; options and stats are fixed-size PODs
+    assert C.sizeof(L.Problem) == 2 * 8 + 7 * 8
+    assert C.sizeof(L.Options) == 4 + 4 + 8 + 4 + 4 + 3 * 8 + 3 * 4 + 5 * 4
+    assert C.sizeof(L.Stats) == 8 * 8 + 4 * 8 + 8 * 4
+
+
+def test_version_and_strerror(lib):
+    assert b"sm_100a" in lib.mpqc_t_version()
+    assert lib.mpqc_t_strerror(L.OK) == b"ok"
+    assert b"no CPU fallback" in lib.mpqc_t_strerror(L.ERR_NO_DEVICE)
+
+
+@pytest.mark.parametrize("o", [1, 2, 3, 7, 21])
+def test_unit_enumeration_matches_oracle(lib, o):
+    tr = oc.ijk_triple_list(o)
+    assert lib.mpqc_t_triple_count(o) == len(tr)
+    i, j, k = C.c_int32(), C.c_int32(), C.c_int32()
+    for u, t in enumerate(tr):
+        assert lib.mpqc_t_triple_of_unit(o, u, C.byref(i), C.byref(j), C.byref(k)) == L.OK
+        assert (i.value, j.value, k.value) == t
+    assert lib.mpqc_t_triple_of_unit(o, len(tr), C.byref(i), C.byref(j), C.byref(k)) == L.ERR_BAD_ARG
+
+
+def test_flop_model(lib):
+    assert lib.mpqc_t_flops(63, 297) == pytest.approx(oc.flops(63, 297))
+    # per-unit count times the number of units approaches the 2 o^3 v^3 (v+o) model
+    o, v = 63, 297
+    tot = lib.mpqc_t_unit_flops(o, v) * lib.mpqc_t_triple_count(o)
+    assert tot == pytest.approx(oc.flops(o, v), rel=0.06)
+
+
+def test_bad_arguments_are_reported(lib):
+    e = C.c_double()
+    assert lib.mpqc_t_energy(None, None, C.byref(e), None) == L.ERR_BAD_ARG
+    assert b"NULL" in lib.mpqc_t_last_error()
+    h = C.c_void_p()
+    assert lib.mpqc_t_create(C.byref(h), 0, 5, 0) == L.ERR_BAD_ARG
+    assert lib.mpqc_t_create(None, 2, 5, 0) == L.ERR_BAD_ARG
+    assert lib.mpqc_t_destroy(None) == L.OK
+
+
+@pytest.mark.skipif(HAS_GPU, reason="checks the loud failure on a box without a GPU")
+def test_no_gpu_means_error_not_fallback(lib):
+    from mpqc_b200.synthetic import make_problem
+    from mpqc_b200.ccsd_t import CCSD_T, DenseCCSD, FeatureDisabled
+    p = make_problem(2, 3)
+    prob = L.make_problem(2, 3, p["eps_occ"], p["eps_vir"], p["t1"], p["t2"], p["g_abij"], p["g_aijk"], p["g_abci"])
+    e = C.c_double(123.0)
+    assert lib.mpqc_t_energy(C.byref(prob), None, C.byref(e), None) == L.ERR_NO_DEVICE
+    h = C.c_void_p()
+    assert lib.mpqc_t_create(C.byref(h), 2, 3, 0) == L.ERR_NO_DEVICE
+    with pytest.raises(FeatureDisabled):
+        CCSD_T({"type": "CCSD(T)"}, ccsd=DenseCCSD.from_problem(p)).compute_ccsd_t()
+
+
+def test_make_problem_validates_shapes():
+    from mpqc_b200.synthetic import make_problem
+    p = make_problem(2, 3)
+    with pytest.raises(ValueError):
+        L.make_problem(2, 3, p["eps_occ"], p["eps_vir"], p["t1"].T.copy(), p["t2"], p["g_abij"], p["g_aijk"], p["g_abci"])
+    with pytest.raises(ValueError):
+        L.make_problem(2, 3, p["eps_occ"], p["eps_vir"], p["t1"].astype(np.float32), p["t2"], p["g_abij"],
+                       p["g_aijk"], p["g_abci"])

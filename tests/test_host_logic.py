@@ -1,0 +1,109 @@
+"""CPU tests of the host-side mirror of the reference interface and of the multi-rank sharding
+(world_size-2 gloo): KeyVal keywords, error behaviour, unit sharding + final sum."""
+import io
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mpqc_b200.ccsd_t import (CCSD_T, DenseCCSD, Energy, FeatureDisabled, InputError, TRange1Engine, class_ptr)
+from mpqc_b200.synthetic import make_problem
+from oracle import ccsd_t_oracle as oc
+
+
+def test_keyval_keywords_and_defaults():
+    w = CCSD_T({"type": "CCSD(T)"})
+    assert w.approach_ == "gpu" and w.occ_block_size_ == 8 and w.unocc_block_size_ == 8
+    assert not w.reblock_ and not w.reblock_inner_ and w.increase_ == 2 and w.n_laplace_quad_ == 4
+    # the reference's golden input (tests/validation/reference/inputs/h2o-ccsd_t-631g-pvdz.json:34-38)
+    w = CCSD_T({"type": "CCSD(T)", "method": "df", "approach": "straight", "occ_block_size": 4,
+                "unocc_block_size": 4, "reblock_occ": 4, "reblock_unocc": 4})
+    assert w.approach_ == "straight" and w.reblock_ and w.occ_block_size_ == 4
+    w = CCSD_T({"approach": "laplace", "reblock_occ": 4, "reblock_inner": 7, "quadrature_points": 3})
+    assert not w.reblock_ and not w.reblock_inner_ and w.n_laplace_quad_ == 3      # ccsd_t.h:125-128
+
+
+def test_invalid_approach_raises_input_error():
+    with pytest.raises(InputError) as ei:
+        CCSD_T({"type": "CCSD(T)", "approach": "medium"})
+    assert ei.value.keyword == "approach" and "Invalid (T) approach" in str(ei.value)     # ccsd_t.h:118-122
+    with pytest.raises(InputError):
+        class_ptr({"type": "CCSD(Q)"})
+    with pytest.raises(InputError):
+        CCSD_T({"rank": 2, "world_size": 2})
+    assert isinstance(class_ptr({"type": "CCSD(T)"}), CCSD_T)
+
+
+def test_laplace_is_feature_disabled():
+    p = make_problem(2, 3)
+    w = CCSD_T({"approach": "laplace"}, ccsd=DenseCCSD.from_problem(p), out=io.StringIO())
+    with pytest.raises(FeatureDisabled):
+        w.compute_ccsd_t()
+
+
+def test_trange1_engine_and_frozen_core_slicing():
+    eng = TRange1Engine(n_occ=5, n_all=13, n_frozen=1)
+    assert (eng.get_occ(), eng.get_nfrozen(), eng.get_active_occ(), eng.get_vir()) == (5, 1, 4, 8)
+    p = make_problem(4, 8)
+    cc = DenseCCSD.from_problem(p, n_frozen=1)
+    eps = cc.orbital_energy()
+    assert len(eps) == 13
+    np.testing.assert_array_equal(eps[1:5], p["eps_occ"])       # eps[i + n_frozen]  (ccsd_t.h:2306-2311)
+    np.testing.assert_array_equal(eps[5:], p["eps_vir"])        # eps[a + n_occ]
+    with pytest.raises(InputError):
+        DenseCCSD(p["t1"], p["t2"], p["g_abij"], p["g_aijk"], p["g_abci"], eps[:-1], 1)
+
+
+def test_obsolete_resets_state():
+    w = CCSD_T({})
+    w.triples_energy_, w.computed_ = -1.0, True
+    w.obsolete()
+    assert w.triples_energy() == 0.0 and not w.computed()
+    assert w.can_evaluate(Energy()) and not w.can_evaluate(object())
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _rank_main(rank, world, port, o, v, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    p = make_problem(o, v)
+    args = (p["t1"], p["t2"], p["g_abij"], p["g_aijk"], p["g_abci"], p["eps_occ"], p["eps_vir"])
+    # the shard this rank's CCSD_T would hand to mpqc_t_energy: unit_first=rank, unit_stride=world
+    w = CCSD_T({"rank": rank, "world_size": world})
+    units = oc.ijk_triple_list(o)[w.rank_::w.world_size_]
+    partial = oc.ijk_driven(*args, triples=units)       # stand-in for the device result of that shard
+    t = torch.tensor([partial], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)            # replaces gop.sum (ccsd_t.h:692); NCCL on the GPU box
+    q.put((rank, len(units), float(t[0])))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_gloo():
+    o, v = 4, 6
+    p = make_problem(o, v)
+    ref = oc.coarse(p["t1"], p["t2"], p["g_abij"], p["g_aijk"], p["g_abci"], p["eps_occ"], p["eps_vir"])
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, o, v, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for pr in procs:
+        pr.join(timeout=60)
+    n_units = sum(r[1] for r in res)
+    assert n_units == o * (o + 1) * (o + 2) // 6 - o
+    for r in res:
+        assert abs(r[2] - ref) < 1e-12

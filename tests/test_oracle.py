@@ -1,0 +1,113 @@
+"""CPU tests of the oracle (no GPU): the three restatements of the reference's (T) agree with each
+other, with the plain-C restatement and with the committed golden vectors; reducer weights and the
+round-robin split follow ccsd_t.h."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from mpqc_b200.synthetic import make_problem
+from oracle import ccsd_t_oracle as oc
+from oracle.c_oracle import straight_c
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "synthetic_*.npz")))
+TOL = 1e-12   # Eh; |E| ~ 0.1-0.3 for the calibrated synthetic inputs
+
+
+def _args(p):
+    return (p["t1"], p["t2"], p["g_abij"], p["g_aijk"], p["g_abci"], p["eps_occ"], p["eps_vir"])
+
+
+@pytest.mark.parametrize("o,v", [(2, 3), (3, 5), (4, 7)])
+def test_three_restatements_agree(o, v):
+    p = make_problem(o, v)
+    ea = oc.straight(*_args(p))
+    eb = oc.coarse(*_args(p), vir_block=8)
+    eb3 = oc.coarse(*_args(p), vir_block=3)     # ragged blocking: exercises ReduceSymm on edge blocks
+    ec = oc.ijk_driven(*_args(p))
+    assert abs(ea - eb) < TOL and abs(ea - eb3) < TOL and abs(ea - ec) < TOL
+
+
+@pytest.mark.parametrize("o,v,nf", [(3, 4, 0), (2, 5, 2)])
+def test_c_restatement_matches_numpy(o, v, nf):
+    p = make_problem(o, v)
+    eps = np.concatenate([np.linspace(-20, -10, nf), p["eps_occ"], p["eps_vir"]])
+    e_c = straight_c(p["t1"], p["t2"], p["g_abij"], p["g_aijk"], p["g_abci"], eps, nf, 0)
+    e_c_symm = straight_c(p["t1"], p["t2"], p["g_abij"], p["g_aijk"], p["g_abci"], eps, nf, 1)
+    e_np = oc.straight(*_args(p))
+    assert abs(e_c - e_np) < TOL
+    assert abs(e_c_symm - e_np) < TOL      # a>=b>=c with weights 2/1/0 == full sum / 3
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(g) for g in GOLDEN])
+def test_golden_vectors(path):
+    g = np.load(path)
+    o, v = int(g["o"]), int(g["v"])
+    p = make_problem(o, v, seed=int(g["seed"]))
+    chk = np.array([p[k].sum() for k in ("t1", "t2", "g_abij", "g_aijk", "g_abci")])
+    np.testing.assert_allclose(chk, g["checksum"], rtol=1e-12)
+    if o ** 3 * v ** 3 > 2e6:
+        pytest.skip("large golden is exercised by the GPU parity test")
+    e, parts = oc.ijk_driven(*_args(p), return_parts=True)
+    assert abs(e - float(g["e_ijk"])) < TOL
+    np.testing.assert_allclose(parts, g["unit_e"], atol=TOL)
+    assert abs(oc.coarse(*_args(p)) - float(g["e_coarse"])) < TOL
+
+
+def test_round_robin_split_sums_to_total():
+    # ccsd_t.h:477-480: rank r takes global_iter % size == r, partial energies add up (gop.sum :692)
+    p = make_problem(3, 9)
+    tot = oc.coarse(*_args(p), vir_block=3)
+    parts = [oc.coarse(*_args(p), vir_block=3, rank=r, size=3) for r in range(3)]
+    assert abs(sum(parts) - tot) < TOL
+    assert all(abs(x) > 0 for x in parts)
+
+
+def test_reducer_weights():
+    # ReduceSymm == plain reduce on a symmetric tile with weights 2/1/0 (:2399-2423)
+    rng = np.random.default_rng(1)
+    o, v = 2, 4
+    t = rng.standard_normal((v, v, v, o, o, o))
+    # symmetrise under simultaneous pair permutation so restricted and full sums must agree
+    s = sum(np.einsum(f"{spec}->abcijk", t) for spec in
+            ("abcijk", "acbikj", "cabkij", "cbakji", "bcajki", "bacjik"))
+    eo = np.sort(rng.uniform(-1.5, -0.3, o)); ev = np.sort(rng.uniform(0.2, 3.0, v))
+    full = oc.reduce_plain(s, eo, ev, (0,) * 6)
+    diag = sum(s[a, a, a] / oc._denominator(eo, ev, np.array([a]), np.array([a]), np.array([a]))[0, 0, 0]
+               for a in range(v)).sum()
+    symm = oc.reduce_symm(s, eo, ev, (0,) * 6)
+    # full = 3*symm + diag  (6 perms*1/2... weight 2 for distinct (6 copies), 1 for two-equal (3 copies))
+    assert abs(full - (3.0 * symm + diag)) < 1e-10
+
+
+def test_triple_enumeration_and_weights():
+    o = 5
+    tr = oc.ijk_triple_list(o)
+    assert len(tr) == o * (o + 1) * (o + 2) // 6 - o
+    assert all(i >= j >= k and not (i == j == k) for (i, j, k) in tr)
+    assert oc.triple_weight(3, 2, 1) == 2.0 and oc.triple_weight(3, 3, 1) == 1.0
+    assert oc.triple_weight(3, 1, 1) == 1.0 and oc.triple_weight(2, 2, 2) == 0.0
+
+
+def test_relabeling_invariance():
+    # E(T) is invariant under a consistent relabeling of virtuals and occupieds
+    o, v = 3, 6
+    p = make_problem(o, v)
+    e0 = oc.ijk_driven(*_args(p))
+    rng = np.random.default_rng(5)
+    pv, po = rng.permutation(v), rng.permutation(o)
+    q = dict(t1=p["t1"][pv][:, po], t2=p["t2"][pv][:, pv][:, :, po][:, :, :, po],
+             g_abij=p["g_abij"][pv][:, pv][:, :, po][:, :, :, po],
+             g_aijk=p["g_aijk"][pv][:, po][:, :, po][:, :, :, po],
+             g_abci=p["g_abci"][pv][:, pv][:, :, pv][:, :, :, po],
+             eps_occ=p["eps_occ"][po], eps_vir=p["eps_vir"][pv])
+    q = {k: np.ascontiguousarray(a) for k, a in q.items()}
+    assert abs(oc.ijk_driven(*_args(q)) - e0) < TOL
+
+
+def test_single_occupied_is_zero():
+    # o = 1: the only triple is i=j=k whose Z vanishes identically
+    p = make_problem(1, 4)
+    assert abs(oc.straight(*_args(p))) < 1e-14
+    assert oc.ijk_triple_list(1) == []
