@@ -232,7 +232,9 @@ GemmParams gemm_params(const mpqc_t_handle* h, int nbatch, const int* triples_de
 int launch_gemm(mpqc_t_handle* h, int nbatch, const int* triples_dev) {
   GemmParams P = gemm_params(h, nbatch, triples_dev);
   int grid = std::min(h->num_sms, P.total_tiles);
-  w_contract_dmma_kernel<<<grid, kGemmThreads, kGemmSmemBytes, h->stream>>>(h->tmA_n, h->tmA_t, h->tmB, P);
+  GemmKernelFn fn = gemm_kernel_for(h->nfrag);
+  MPQC_T_CHECK(fn != nullptr, MPQC_T_ERR_INTERNAL, "no W-contraction kernel for this column-fragment count");
+  fn<<<grid, kGemmThreads, kGemmSmemBytes, h->stream>>>(h->tmA_n, h->tmA_t, h->tmB, P);
   MPQC_T_CUDA(cudaGetLastError());
   return MPQC_T_OK;
 }
@@ -252,7 +254,7 @@ int launch_energy(mpqc_t_handle* h, int nbatch, const int* triples_dev, double* 
   E.eps_vir = h->eps_vir;
   E.tile_sets = h->tile_sets;
   E.partial = h->partial;
-  t_energy_fused_kernel<<<dim3((unsigned)h->ntt, (unsigned)nbatch), kEThreads, 0, h->stream>>>(E);
+  t_energy_fused_kernel<<<dim3((unsigned)h->ntt, (unsigned)nbatch), kEThreads, kEnergySmemBytes, h->stream>>>(E);
   MPQC_T_CUDA(cudaGetLastError());
   t_energy_finish_kernel<<<nbatch, 256, 0, h->stream>>>(h->partial, h->ntt, triples_dev, unit_e_dev);
   MPQC_T_CUDA(cudaGetLastError());
@@ -553,8 +555,11 @@ int mpqc_t_create(mpqc_t_handle** out, int64_t o, int64_t v, int32_t device) {
         }
     MPQC_T_CUDA(cudaMalloc(&h->tile_sets, sets.size()));
     MPQC_T_CUDA(cudaMemcpy(h->tile_sets, sets.data(), sets.size(), cudaMemcpyHostToDevice));
-    MPQC_T_CUDA(cudaFuncSetAttribute(w_contract_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     kGemmSmemBytes));
+    GemmKernelFn fn = gemm_kernel_for(h->nfrag);
+    MPQC_T_CHECK(fn != nullptr, MPQC_T_ERR_INTERNAL, "no W-contraction kernel for this column-fragment count");
+    MPQC_T_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+    MPQC_T_CUDA(cudaFuncSetAttribute(t_energy_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kEnergySmemBytes));
     return MPQC_T_OK;
   }();
   if (rc != MPQC_T_OK) {

@@ -11,10 +11,13 @@
 //   Z[a,b,c]  = 4 W[abc] + W[bca] + W[cab] - 2 (W[cba] + W[acb] + W[bac])
 //   E_ijk     = sum_abc (W+V) Z / (e_i + e_j + e_k - e_a - e_b - e_c)
 //
-// A block owns one unordered set of three 8-wide virtual tiles {TA >= TB >= TC}: the six permuted
-// 8x8x8 tiles of each N_g are read exactly once from HBM/L2 (64-byte row segments), transposed
-// in shared memory, and every (a,b,c) of the distinct permuted tiles is evaluated from shared
-// memory.  HBM-bound: algorithmic bytes = 3 arrays * 8 v^3 per triple.
+// A block owns one unordered set of three 8-wide virtual tiles {TA >= TB >= TC}.  The 18 raw 8x8x8
+// tiles it needs (6 permuted tile coordinates x 3 arrays) are fetched ONCE from HBM/L2 with cp.async
+// (16-byte chunks, zero-filled outside the tensor) into XOR-swizzled shared memory, all in flight at
+// once.  A thread then owns an element triple (a,b,c) of the (TA,TB,TC) tile and evaluates all six
+// permutations of it from shared memory: the six W values are read once, the denominator (symmetric
+// in a,b,c) is divided once.  When tiles coincide every element is visited `mult` times (2 or 6), so
+// the block sum is scaled by 1/mult.  HBM-bound: algorithmic bytes = 3 arrays * 8 v^3 per triple.
 #pragma once
 
 #include "common.cuh"
@@ -23,6 +26,10 @@ namespace mpqc_t {
 
 constexpr int kET = 8;              // energy tile edge
 constexpr int kEThreads = 256;
+constexpr int kETileElems = kET * kET * kET;                 // 512 doubles
+constexpr int kEStageBytes = 18 * kETileElems * 8;           // 73,728 B of raw tiles
+constexpr int kESmallDoubles = 27 * 64 + 72 + 24 + 8;        // g patches, t1 slices, eps slices, reduction
+constexpr int kEnergySmemBytes = kEStageBytes + kESmallDoubles * 8;
 
 struct EnergyParams {
   int v, o, ldw;
@@ -39,142 +46,127 @@ struct EnergyParams {
 };
 
 // the six permutations s = (s0,s1,s2): tile coordinates (X,Y,Z) = (T[s0], T[s1], T[s2])
-__constant__ int8_t c_perm[6][3] = {{0, 1, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}, {0, 2, 1}, {1, 0, 2}};
+#define MPQC_T_PERMS {{0, 1, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}, {0, 2, 1}, {1, 0, 2}}
 
-__device__ __forceinline__ int perm_index(int s0, int s1, int s2) {
-  // inverse of c_perm
-  if (s0 == 0) return s1 == 1 ? 0 : 4;
-  if (s0 == 1) return s1 == 2 ? 1 : 5;
-  return s1 == 0 ? 2 : 3;
+__host__ __device__ constexpr int perm_index(int s0, int s1) {
+  return s0 == 0 ? (s1 == 1 ? 0 : 4) : (s0 == 1 ? (s1 == 2 ? 1 : 5) : (s1 == 0 ? 2 : 3));
 }
 
-__global__ void __launch_bounds__(kEThreads)
-t_energy_fused_kernel(const EnergyParams P) {
-  // W tiles of the six permuted tile coordinates; [perm][a][b][c] with a padded fastest pitch
-  __shared__ double Wt[6][kET][kET][kET + 1];
-  __shared__ double Gs[3][3][3][kET][kET];   // [ij|jk|ik][row tile][col tile][.][.]
-  __shared__ double T1s[3][3][kET];          // [i|j|k][tile][.]
-  __shared__ double Ev[3][kET];
-  __shared__ double red[kEThreads / 32];
+// swizzled position of element (x,y,z) inside an 8x8x8 tile: rows (x,y) of 8 doubles; adjacent rows
+// are swapped and the 16-byte chunk index is XORed so that reads with any one of x,y,z varying fastest
+// across the lanes spread over the banks.  Bits 1-2 of z only are permuted, so a (z even, z+1) pair
+// stays one contiguous 16-byte chunk (the cp.async granule).
+__device__ __forceinline__ int sw_idx(int x, int y, int z) {
+  const int row = ((x << 3) | y) ^ (((y >> 2) ^ x) & 1);
+  return (row << 3) | (z ^ (((y ^ (x >> 1)) & 3) << 1));
+}
 
+__device__ __forceinline__ void cp_async_16_zfill(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(kEThreads, 2)
+t_energy_fused_kernel(const EnergyParams P) {
+  extern __shared__ __align__(16) uint8_t esmem[];
+  double* S = reinterpret_cast<double*>(esmem);                 // [3 arrays][6 perms][512] swizzled
+  double* Gs = S + 18 * kETileElems;                            // [3][3][3][8][8]
+  double* T1s = Gs + 27 * 64;                                   // [3][3][8]
+  double* Ev = T1s + 72;                                        // [3][8]
+  double* red = Ev + 24;                                        // [8]
+
+  constexpr int PERM[6][3] = MPQC_T_PERMS;
   const int b = blockIdx.y;
   const int tt = blockIdx.x;
   const int tid = threadIdx.x;
   const int i = P.triples[3 * b], j = P.triples[3 * b + 1], k = P.triples[3 * b + 2];
-  int T[3] = {P.tile_sets[4 * tt], P.tile_sets[4 * tt + 1], P.tile_sets[4 * tt + 2]};
+  const int T[3] = {P.tile_sets[4 * tt], P.tile_sets[4 * tt + 1], P.tile_sets[4 * tt + 2]};
   const int v = P.v, ldw = P.ldw;
-  const double* n0 = P.w + (int64_t)(b * 3) * v * v * ldw;
-  const double* n1 = n0 + (int64_t)v * v * ldw;
-  const double* n2 = n1 + (int64_t)v * v * ldw;
+  const double* nbase = P.w + (int64_t)(b * 3) * v * v * ldw;
+  const int64_t nstride = (int64_t)v * v * ldw;
 
-  // ---- small operands: g_ij / g_jk / g_ik patches, t1 and eps slices ----
-  for (int e = tid; e < 3 * 3 * 3 * 64; e += kEThreads) {
-    int c = e & 7, r = (e >> 3) & 7, tcol = (e >> 6) % 3, trow = (e / 192) % 3, which = e / 576;
-    int x = which == 0 ? i : (which == 1 ? j : i);
-    int y = which == 0 ? j : k;
-    int gr = T[trow] * kET + r, gc = T[tcol] * kET + c;
-    double val = 0.0;
-    if (gr < v && gc < v) val = __ldg(P.gv + ((int64_t)(x * P.o + y) * v + gr) * v + gc);
-    Gs[which][trow][tcol][r][c] = val;
-  }
-  if (tid < 72) {
-    int c = tid & 7, t = (tid >> 3) % 3, which = tid / 24;
-    int x = which == 0 ? i : (which == 1 ? j : k);
-    int gc = T[t] * kET + c;
-    T1s[which][t][c] = gc < v ? __ldg(P.t1t + (int64_t)x * v + gc) : 0.0;
-  } else if (tid >= 96 && tid < 120) {
-    int c = tid & 7, t = (tid - 96) >> 3;
-    int gc = T[t] * kET + c;
-    Ev[t][c] = gc < v ? __ldg(P.eps_vir + gc) : 0.0;
-  }
-
-  // ---- phase 1: Wt[pi][a][b][c] = N_0[a][b][c]   (rows (a,b), c contiguous) ----
-  // 6 perms * 64 rows * 4 double2 = 1536 vector loads, 6 per thread
+  // ---- issue all 18 raw-tile copies: thread -> (row = tid>>2, 16-byte chunk = tid&3) of every tile ----
+  {
+    const int row = tid >> 2, x = row >> 3, y = row & 7, z = (tid & 3) << 1;
+    const uint32_t s_base = smem_u32(S);
+    const uint32_t dst_off = (uint32_t)sw_idx(x, y, z) * 8u;
 #pragma unroll
-  for (int it = 0; it < 6; ++it) {
-    int e = it * kEThreads + tid;
-    int c2 = (e & 3) * 2, row = (e >> 2) & 63, pi = e >> 8;
-    int la = row >> 3, lb = row & 7;
-    int X = T[c_perm[pi][0]], Y = T[c_perm[pi][1]], Z = T[c_perm[pi][2]];
-    int ga = X * kET + la, gb = Y * kET + lb, gc = Z * kET + c2;
-    double2 val = make_double2(0.0, 0.0);
-    if (ga < v && gb < v && gc < v) {
-      const double* src = n0 + ((int64_t)ga * v + gb) * ldw + gc;
-      val = __ldg(reinterpret_cast<const double2*>(src));   // ldw even, gc even -> 16B aligned
-      if (gc + 1 >= v) val.y = 0.0;
-    }
-    Wt[pi][la][lb][c2] = val.x;
-    Wt[pi][la][lb][c2 + 1] = val.y;
-  }
-  __syncthreads();
-  // ---- phase 2: Wt[pi][a][b][c] += N_1[a][c][b]   (rows (a,c), b contiguous) ----
+    for (int pi = 0; pi < 6; ++pi) {
+      const int X = T[PERM[pi][0]], Y = T[PERM[pi][1]], Z = T[PERM[pi][2]];
+      // array 0 tile at (X,Y,Z); array 1 tile at (X,Z,Y); array 2 tile at (Z,Y,X)   [first][second][third]
 #pragma unroll
-  for (int it = 0; it < 6; ++it) {
-    int e = it * kEThreads + tid;
-    int b2 = (e & 3) * 2, row = (e >> 2) & 63, pi = e >> 8;
-    int la = row >> 3, lc = row & 7;
-    int X = T[c_perm[pi][0]], Y = T[c_perm[pi][1]], Z = T[c_perm[pi][2]];
-    int ga = X * kET + la, gc = Z * kET + lc, gb = Y * kET + b2;
-    double2 val = make_double2(0.0, 0.0);
-    if (ga < v && gc < v && gb < v) {
-      const double* src = n1 + ((int64_t)ga * v + gc) * ldw + gb;
-      val = __ldg(reinterpret_cast<const double2*>(src));
-      if (gb + 1 >= v) val.y = 0.0;
-    }
-    Wt[pi][la][b2][lc] += val.x;
-    Wt[pi][la][b2 + 1][lc] += val.y;
-  }
-  __syncthreads();
-  // ---- phase 3: Wt[pi][a][b][c] += N_2[c][b][a]   (rows (c,b), a contiguous) ----
-#pragma unroll
-  for (int it = 0; it < 6; ++it) {
-    int e = it * kEThreads + tid;
-    int a2 = (e & 3) * 2, row = (e >> 2) & 63, pi = e >> 8;
-    int lc = row >> 3, lb = row & 7;
-    int X = T[c_perm[pi][0]], Y = T[c_perm[pi][1]], Z = T[c_perm[pi][2]];
-    int gc = Z * kET + lc, gb = Y * kET + lb, ga = X * kET + a2;
-    double2 val = make_double2(0.0, 0.0);
-    if (gc < v && gb < v && ga < v) {
-      const double* src = n2 + ((int64_t)gc * v + gb) * ldw + ga;
-      val = __ldg(reinterpret_cast<const double2*>(src));
-      if (ga + 1 >= v) val.y = 0.0;
-    }
-    Wt[pi][a2][lb][lc] += val.x;
-    Wt[pi][a2 + 1][lb][lc] += val.y;
-  }
-  __syncthreads();
-
-  // ---- evaluate every element of the distinct permuted tiles ----
-  const double eijk = __ldg(P.eps_occ + i) + __ldg(P.eps_occ + j) + __ldg(P.eps_occ + k);
-  double sum = 0.0;
-#pragma unroll 1
-  for (int pi = 0; pi < 6; ++pi) {
-    const int s0 = c_perm[pi][0], s1 = c_perm[pi][1], s2 = c_perm[pi][2];
-    // skip a permutation whose tile coordinates repeat an earlier one (TA==TB and/or TB==TC)
-    bool dup = false;
-    for (int pj = 0; pj < pi; ++pj)
-      dup |= (T[c_perm[pj][0]] == T[s0]) && (T[c_perm[pj][1]] == T[s1]) && (T[c_perm[pj][2]] == T[s2]);
-    if (dup) continue;
-    // element permutations: W[b,c,a] lives in the tile with coordinates (Y,Z,X) = perm (s1,s2,s0), ...
-    const int p_bca = perm_index(s1, s2, s0), p_cab = perm_index(s2, s0, s1);
-    const int p_cba = perm_index(s2, s1, s0), p_acb = perm_index(s0, s2, s1);
-    const int p_bac = perm_index(s1, s0, s2);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int e = h * kEThreads + tid;
-      const int lc = e & 7, lb = (e >> 3) & 7, la = e >> 6;
-      const int ga = T[s0] * kET + la, gb = T[s1] * kET + lb, gc = T[s2] * kET + lc;
-      if (ga < v && gb < v && gc < v) {
-        const double w = Wt[pi][la][lb][lc];
-        const double z = 4.0 * w + Wt[p_bca][lb][lc][la] + Wt[p_cab][lc][la][lb] -
-                         2.0 * (Wt[p_cba][lc][lb][la] + Wt[p_acb][la][lc][lb] + Wt[p_bac][lb][la][lc]);
-        const double vv = Gs[0][s0][s1][la][lb] * T1s[2][s2][lc] + Gs[1][s1][s2][lb][lc] * T1s[0][s0][la] +
-                          Gs[2][s0][s2][la][lc] * T1s[1][s1][lb];
-        const double d = eijk - Ev[s0][la] - Ev[s1][lb] - Ev[s2][lc];
-        sum += (w + vv) * z / d;
+      for (int g = 0; g < 3; ++g) {
+        const int t0 = g == 2 ? Z : X, t1 = g == 1 ? Z : Y, t2 = g == 0 ? Z : (g == 1 ? Y : X);
+        const int g0 = t0 * kET + x, g1 = t1 * kET + y, g2 = t2 * kET + z;
+        int nbytes = 0;
+        if (g0 < v && g1 < v && g2 < v) nbytes = (g2 + 1 < v) ? 16 : 8;
+        const double* src = nbase + g * nstride + ((int64_t)(g0 < v ? g0 : 0) * v + (g1 < v ? g1 : 0)) * ldw +
+                            (g2 < v ? g2 : 0);
+        cp_async_16_zfill(s_base + (uint32_t)((g * 6 + pi) * kETileElems * 8) + dst_off, src, nbytes);
       }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
+
+  // ---- small operands (L2 resident): g_ij / g_jk / g_ik patches, t1 and eps slices ----
+  for (int e = tid; e < 27 * 64; e += kEThreads) {
+    const int c = e & 7, r = (e >> 3) & 7, tcol = (e >> 6) % 3, trow = (e / 192) % 3, which = e / 576;
+    const int x = which == 1 ? j : i;
+    const int y = which == 0 ? j : k;
+    const int gr = (trow == 0 ? T[0] : (trow == 1 ? T[1] : T[2])) * kET + r;
+    const int gc = (tcol == 0 ? T[0] : (tcol == 1 ? T[1] : T[2])) * kET + c;
+    double val = 0.0;
+    if (gr < v && gc < v) val = __ldg(P.gv + ((int64_t)(x * P.o + y) * v + gr) * v + gc);
+    Gs[e] = val;
+  }
+  if (tid < 72) {
+    const int c = tid & 7, t = (tid >> 3) % 3, which = tid / 24;
+    const int x = which == 0 ? i : (which == 1 ? j : k);
+    const int gc = (t == 0 ? T[0] : (t == 1 ? T[1] : T[2])) * kET + c;
+    T1s[tid] = gc < v ? __ldg(P.t1t + (int64_t)x * v + gc) : 0.0;
+  } else if (tid >= 96 && tid < 120) {
+    const int c = tid & 7, t = (tid - 96) >> 3;
+    const int gc = (t == 0 ? T[0] : (t == 1 ? T[1] : T[2])) * kET + c;
+    Ev[tid - 96] = gc < v ? __ldg(P.eps_vir + gc) : 0.0;
+  }
+  const double eijk = __ldg(P.eps_occ + i) + __ldg(P.eps_occ + j) + __ldg(P.eps_occ + k);
+
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  // ---- evaluate: thread owns (la,lb,lc) of the (TA,TB,TC) tile and all six permutations of it ----
+  double sum = 0.0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int l[3] = {(tid >> 6) + 4 * h, (tid >> 3) & 7, tid & 7};
+    const int ga = T[0] * kET + l[0], gb = T[1] * kET + l[1], gc = T[2] * kET + l[2];
+    if (ga < v && gb < v && gc < v) {
+      double w[6];
+#pragma unroll
+      for (int pi = 0; pi < 6; ++pi) {
+        const int s0 = PERM[pi][0], s1 = PERM[pi][1], s2 = PERM[pi][2];
+        // element (e[s0], e[s1], e[s2]) of W = N_0[.s0.][.s1.][.s2.] + N_1[.s0.][.s2.][.s1.] + N_2[.s2.][.s1.][.s0.]
+        w[pi] = S[(0 * 6 + pi) * kETileElems + sw_idx(l[s0], l[s1], l[s2])] +
+                S[(1 * 6 + pi) * kETileElems + sw_idx(l[s0], l[s2], l[s1])] +
+                S[(2 * 6 + pi) * kETileElems + sw_idx(l[s2], l[s1], l[s0])];
+      }
+      double acc = 0.0;
+#pragma unroll
+      for (int pi = 0; pi < 6; ++pi) {
+        const int s0 = PERM[pi][0], s1 = PERM[pi][1], s2 = PERM[pi][2];
+        const double z = 4.0 * w[pi] + w[perm_index(s1, s2)] + w[perm_index(s2, s0)] -
+                         2.0 * (w[perm_index(s2, s1)] + w[perm_index(s0, s2)] + w[perm_index(s1, s0)]);
+        // V for (a',b',c') = (e[s0], e[s1], e[s2]):  g_ij[a',b'] t1[c',k] + g_jk[b',c'] t1[a',i] + g_ik[a',c'] t1[b',j]
+        const double vv = Gs[((0 * 3 + s0) * 3 + s1) * 64 + l[s0] * 8 + l[s1]] * T1s[(2 * 3 + s2) * 8 + l[s2]] +
+                          Gs[((1 * 3 + s1) * 3 + s2) * 64 + l[s1] * 8 + l[s2]] * T1s[(0 * 3 + s0) * 8 + l[s0]] +
+                          Gs[((2 * 3 + s0) * 3 + s2) * 64 + l[s0] * 8 + l[s2]] * T1s[(1 * 3 + s1) * 8 + l[s1]];
+        acc += (w[pi] + vv) * z;
+      }
+      const double d = eijk - Ev[l[0]] - Ev[8 + l[1]] - Ev[16 + l[2]];
+      sum += acc / d;
+    }
+  }
+  // every element of the distinct permuted tiles was visited mult times
+  const double mult = (T[0] == T[1] && T[1] == T[2]) ? 6.0 : ((T[0] == T[1] || T[1] == T[2]) ? 2.0 : 1.0);
   sum = warp_sum(sum);
   if ((tid & 31) == 0) red[tid >> 5] = sum;
   __syncthreads();
@@ -182,7 +174,7 @@ t_energy_fused_kernel(const EnergyParams P) {
     double s = 0.0;
 #pragma unroll
     for (int wi = 0; wi < kEThreads / 32; ++wi) s += red[wi];
-    P.partial[(int64_t)b * P.ntt + tt] = s;
+    P.partial[(int64_t)b * P.ntt + tt] = s / mult;
   }
 }
 

@@ -11,11 +11,19 @@
 // (the permuted adds happen in the energy kernel's shared-memory tiles, so the reference's five
 // 6-index permutes of ccsd_t.h:498-555 never touch HBM).
 //
-// Machine mapping (sm_100a): persistent grid, one CTA per SM.  One producer warp issues TMA
-// (cp.async.bulk.tensor, 128B-swizzled boxes) into a STAGES-deep shared-memory ring guarded by
-// full/empty mbarriers; eight consumer warps each own a 16-row x (8*nfrag)-column slice of the
-// 128 x tn output tile and issue FP64 tensor-core DMMA.8x8x4 from conflict-free LDS.128 fragment
-// reads.  tcgen05/TMEM has no FP64 kind, so DMMA is the Blackwell tensor path for doubles.
+// Machine mapping (sm_100a): persistent grid, one CTA per SM, three warpgroups.  One producer lane
+// issues TMA (cp.async.bulk.tensor, 128B-swizzled boxes) into a kStages-deep shared-memory ring guarded
+// by full/empty mbarriers; eight consumer warps each own a 16-row x (8*NFRAG)-column slice of the
+// 128 x tn output tile and issue FP64 tensor-core DMMA.8x8x4 from conflict-free LDS.128 fragment reads.
+// tcgen05/TMEM has no FP64 kind, so DMMA is the Blackwell tensor path for doubles.
+//
+// Consumer schedule (what the r01a ncu profile asked for): NFRAG is a template parameter so the k-block
+// body is branch-free; B fragments are processed in register chunks of <= 4 column fragments, double
+// buffered, and the first chunk + A fragments of the NEXT k-block are fetched (after its full-barrier
+// wait) before the last chunk of the current block is issued, so no LDS latency is exposed at block
+// boundaries; within a chunk DMMAs are issued k-step-major so dependent DMMAs on one accumulator are
+// separated by 6-8 independent ones; the half-filled last k-block (Kp % 16 == 8) is a separate
+// instantiation instead of predicated-off DMMAs.
 //
 // Tile rows are a (tp x tq) patch of (p,q); the second term reads the SAME rows from the
 // transposed patch A_x2[q][p][:] with a second TMA box, so no transposed copy of A exists.
@@ -65,11 +73,117 @@ __device__ __forceinline__ void decode_tile(const GemmParams& P, int tile, int& 
   b = t / 3;
 }
 
+// compile-time chunking of the NFRAG column fragments into register chunks of nearly equal size
+template <int NFRAG>
+struct Chunking {
+  static constexpr int kMax = NFRAG <= 13 ? 4 : 3;              // fragments per chunk (register budget)
+  static constexpr int kNum = (NFRAG + kMax - 1) / kMax;        // chunks per k-block
+  __host__ __device__ static constexpr int beg(int c) { return c * NFRAG / kNum; }
+  __host__ __device__ static constexpr int len(int c) { return beg(c + 1) - beg(c); }
+};
+
+struct BFrag {
+  double2 lo, hi;   // kap (2k, 2k+1) and (8+2k, 9+2k) of this lane's B row
+};
+
+template <int NFRAG, int C>
+__device__ __forceinline__ void load_b_chunk(BFrag (&b)[Chunking<NFRAG>::kMax], uint32_t sb) {
+  using CH = Chunking<NFRAG>;
+#pragma unroll
+  for (int u = 0; u < CH::len(C); ++u) {
+    const uint32_t addr = sb + (uint32_t)(CH::beg(C) + u) * 1024u;
+    b[u].lo = lds128(addr);
+    b[u].hi = lds128(addr ^ 64u);
+  }
+}
+
+template <int NFRAG, int C, bool HALF>
+__device__ __forceinline__ void mma_chunk(double (&acc)[2][NFRAG][2], const double2 (&alo)[2], const double2 (&ahi)[2],
+                                          const BFrag (&b)[Chunking<NFRAG>::kMax]) {
+  using CH = Chunking<NFRAG>;
+  constexpr int n0 = CH::beg(C), nl = CH::len(C);
+  // k-step major: consecutive DMMAs touch different accumulators
+#pragma unroll
+  for (int u = 0; u < nl; ++u)
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) dmma884(acc[mi][n0 + u][0], acc[mi][n0 + u][1], alo[mi].x, b[u].lo.x);
+#pragma unroll
+  for (int u = 0; u < nl; ++u)
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) dmma884(acc[mi][n0 + u][0], acc[mi][n0 + u][1], alo[mi].y, b[u].lo.y);
+  if (!HALF) {
+#pragma unroll
+    for (int u = 0; u < nl; ++u)
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) dmma884(acc[mi][n0 + u][0], acc[mi][n0 + u][1], ahi[mi].x, b[u].hi.x);
+#pragma unroll
+    for (int u = 0; u < nl; ++u)
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) dmma884(acc[mi][n0 + u][0], acc[mi][n0 + u][1], ahi[mi].y, b[u].hi.y);
+  }
+}
+
+// state a consumer warp carries across k-blocks
+template <int NFRAG>
+struct ConsumerRegs {
+  double2 alo[2], ahi[2];                         // A fragments of the current k-block
+  BFrag bb[2][Chunking<NFRAG>::kMax];             // double-buffered B chunks
+};
+
+// One k-block.  On entry R holds the A fragments and B chunk 0 (in bb[0]) of this block.  On exit, if
+// has_next, it holds those of the next block (read from stage `ns` after waiting on its full barrier).
+template <int NFRAG, bool HALF>
+__device__ __forceinline__ void kblock(double (&acc)[2][NFRAG][2], ConsumerRegs<NFRAG>& R, uint32_t sb_cur,
+                                       bool has_next, uint64_t* next_full, uint32_t next_phase, uint32_t sa_next,
+                                       uint32_t a0_next, uint32_t a1_next, uint32_t sb_next) {
+  using CH = Chunking<NFRAG>;
+  double2 nlo[2], nhi[2];
+#pragma unroll
+  for (int c = 0; c < CH::kNum; ++c) {
+    if (c + 1 < CH::kNum) {
+      // prefetch the next chunk of this block (template index must be a constant: unrolled switch)
+      if (c == 0) load_b_chunk<NFRAG, (1 < CH::kNum ? 1 : 0)>(R.bb[1], sb_cur);
+      if (c == 1) load_b_chunk<NFRAG, (2 < CH::kNum ? 2 : 0)>(R.bb[0], sb_cur);
+      if (c == 2) load_b_chunk<NFRAG, (3 < CH::kNum ? 3 : 0)>(R.bb[1], sb_cur);
+      if (c == 3) load_b_chunk<NFRAG, (4 < CH::kNum ? 4 : 0)>(R.bb[0], sb_cur);
+      if (c == 4) load_b_chunk<NFRAG, (5 < CH::kNum ? 5 : 0)>(R.bb[1], sb_cur);
+    } else if (has_next) {
+      // last chunk: fetch the next k-block's A fragments and B chunk 0 before issuing this chunk's DMMAs
+      mbar_wait(next_full, next_phase);
+      nlo[0] = lds128(sa_next + a0_next);
+      nlo[1] = lds128(sa_next + a1_next);
+      nhi[0] = lds128(sa_next + (a0_next ^ 64u));
+      nhi[1] = lds128(sa_next + (a1_next ^ 64u));
+      load_b_chunk<NFRAG, 0>(R.bb[(c + 1) & 1], sb_next);
+    }
+    if (c == 0) mma_chunk<NFRAG, 0, HALF>(acc, R.alo, R.ahi, R.bb[0]);
+    if (c == 1) mma_chunk<NFRAG, (1 < CH::kNum ? 1 : 0), HALF>(acc, R.alo, R.ahi, R.bb[1]);
+    if (c == 2) mma_chunk<NFRAG, (2 < CH::kNum ? 2 : 0), HALF>(acc, R.alo, R.ahi, R.bb[0]);
+    if (c == 3) mma_chunk<NFRAG, (3 < CH::kNum ? 3 : 0), HALF>(acc, R.alo, R.ahi, R.bb[1]);
+    if (c == 4) mma_chunk<NFRAG, (4 < CH::kNum ? 4 : 0), HALF>(acc, R.alo, R.ahi, R.bb[0]);
+    if (c == 5) mma_chunk<NFRAG, (5 < CH::kNum ? 5 : 0), HALF>(acc, R.alo, R.ahi, R.bb[1]);
+  }
+  if (has_next) {
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+      R.alo[mi] = nlo[mi];
+      R.ahi[mi] = nhi[mi];
+    }
+    if (CH::kNum & 1) {   // chunk 0 of the next block was loaded into bb[1]; the next block expects bb[0]
+#pragma unroll
+      for (int u = 0; u < CH::kMax; ++u) R.bb[0][u] = R.bb[1][u];
+    }
+  }
+}
+
+template <int NFRAG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 w_contract_dmma_kernel(const __grid_constant__ CUtensorMap tmA_n,   // box (16, tq, tp, 1)
                        const __grid_constant__ CUtensorMap tmA_t,   // box (16, tp, tq, 1)
                        const __grid_constant__ CUtensorMap tmB,     // box (16, tn, 1)
                        const GemmParams P) {
+  static_assert(NFRAG >= 1 && NFRAG <= kMaxNFrag, "NFRAG out of range");
+  static_assert(Chunking<NFRAG>::kNum <= 6, "chunk dispatch covers at most 6 chunks");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -140,8 +254,8 @@ w_contract_dmma_kernel(const __grid_constant__ CUtensorMap tmA_n,   // box (16, 
 
   // B fragment row offsets are tile independent: tile column 8*ni + sigma(g8)
   //   byte offset of chunk c in row r: r*128 + ((c ^ (r & 7)) << 4)
-  const uint32_t b_lo_off = (uint32_t)sg * 128u + (uint32_t)((kq ^ sg) << 4);   // + ni * 1024
-  // rows of this thread for the normal term: m = 16*warp + 8*mi + sigma(g8)
+  const uint32_t b_lo_off = (uint32_t)kAStageBytes + (uint32_t)sg * 128u + (uint32_t)((kq ^ sg) << 4);
+  // rows of this thread: m = 16*warp + 8*mi + sigma(g8); offsets inside the normal / transposed box
   uint32_t a_off_n[2], a_off_t[2];
 #pragma unroll
   for (int mi = 0; mi < 2; ++mi) {
@@ -151,62 +265,49 @@ w_contract_dmma_kernel(const __grid_constant__ CUtensorMap tmA_n,   // box (16, 
     int srow = (mm % P.tq) * P.tp + (mm / P.tq);     // row of (p,q) inside the transposed box
     a_off_t[mi] = (uint32_t)srow * 128u + (uint32_t)((kq ^ (srow & 7)) << 4);
   }
-  const int nfrag = P.nfrag;
+  const int kblocks = P.kblocks;
+  const int nblk = 2 * kblocks;                       // k-blocks per tile (two terms)
+  const bool half_last = (P.Kp % kBK) != 0;            // Kp % 16 == 8: last block of a term is half filled
 
   int stage = 0;
   uint32_t phase = 0;
+  ConsumerRegs<NFRAG> R;
+  if ((int)blockIdx.x < P.total_tiles) {
+    // prologue: fragments of the very first k-block
+    mbar_wait(&full_bar[0], 0);
+    R.alo[0] = lds128(smem_base + a_off_n[0]);
+    R.alo[1] = lds128(smem_base + a_off_n[1]);
+    R.ahi[0] = lds128(smem_base + (a_off_n[0] ^ 64u));
+    R.ahi[1] = lds128(smem_base + (a_off_n[1] ^ 64u));
+    load_b_chunk<NFRAG, 0>(R.bb[0], smem_base + b_lo_off);
+  }
   for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-    double acc[2][kMaxNFrag][2];
+    double acc[2][NFRAG][2];
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-      for (int ni = 0; ni < kMaxNFrag; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+      for (int ni = 0; ni < NFRAG; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    const bool more_tiles = tile + (int)gridDim.x < P.total_tiles;
 
-    for (int term = 0; term < 2; ++term) {
-      const uint32_t a0 = term == 0 ? a_off_n[0] : a_off_t[0];
-      const uint32_t a1 = term == 0 ? a_off_n[1] : a_off_t[1];
-      for (int kb = 0; kb < P.kblocks; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
-        const uint32_t sa = smem_base + stage * kStageBytes;
-        const uint32_t sb = sa + kAStageBytes + b_lo_off;
-        const bool second_half = (kb * kBK + 8) < P.Kp;   // kap 8..15 of this block exist
-        double2 alo[2], ahi[2];
-        alo[0] = lds128(sa + a0);
-        alo[1] = lds128(sa + a1);
-        ahi[0] = lds128(sa + (a0 ^ 64u));
-        ahi[1] = lds128(sa + (a1 ^ 64u));
-#pragma unroll
-        for (int nc = 0; nc < kMaxNFrag; nc += 4) {
-          if (nc < nfrag) {
-            double2 blo[4], bhi[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              blo[u] = lds128(sb + (nc + u) * 1024u);
-              bhi[u] = lds128((sb + (nc + u) * 1024u) ^ 64u);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (nc + u < nfrag) {
-#pragma unroll
-                for (int mi = 0; mi < 2; ++mi) {
-                  dmma884(acc[mi][nc + u][0], acc[mi][nc + u][1], alo[mi].x, blo[u].x);
-                  dmma884(acc[mi][nc + u][0], acc[mi][nc + u][1], alo[mi].y, blo[u].y);
-                }
-                if (second_half) {
-#pragma unroll
-                  for (int mi = 0; mi < 2; ++mi) {
-                    dmma884(acc[mi][nc + u][0], acc[mi][nc + u][1], ahi[mi].x, bhi[u].x);
-                    dmma884(acc[mi][nc + u][0], acc[mi][nc + u][1], ahi[mi].y, bhi[u].y);
-                  }
-                }
-              }
-            }
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[stage]);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
-      }
+    for (int q = 0; q < nblk; ++q) {
+      const bool last_in_tile = (q == nblk - 1);
+      const bool has_next = !last_in_tile || more_tiles;
+      const bool next_transposed = !last_in_tile && (q + 1 >= kblocks);
+      const int ns = (stage + 1 == kStages) ? 0 : stage + 1;
+      const uint32_t nph = (ns == 0) ? (phase ^ 1u) : phase;
+      const uint32_t sa_next = smem_base + ns * kStageBytes;
+      const uint32_t a0n = next_transposed ? a_off_t[0] : a_off_n[0];
+      const uint32_t a1n = next_transposed ? a_off_t[1] : a_off_n[1];
+      const uint32_t sb_cur = smem_base + stage * kStageBytes + b_lo_off;
+      const bool half = half_last && (q == kblocks - 1 || q == nblk - 1);
+      if (half)
+        kblock<NFRAG, true>(acc, R, sb_cur, has_next, &full_bar[ns], nph, sa_next, a0n, a1n, sa_next + b_lo_off);
+      else
+        kblock<NFRAG, false>(acc, R, sb_cur, has_next, &full_bar[ns], nph, sa_next, a0n, a1n, sa_next + b_lo_off);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      stage = ns;
+      phase = nph;
     }
 
     // ---- epilogue: registers -> N_g[p][q][r0 + col] (32-byte sector-aligned runs) ----
@@ -217,12 +318,12 @@ w_contract_dmma_kernel(const __grid_constant__ CUtensorMap tmA_n,   // box (16, 
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi) {
       const int m = 16 * warp + 8 * mi + sg;
-      const int p = p0 + m / P.tq, q = q0 + m % P.tq;
-      const bool row_ok = (m < P.rows_valid) && (p < P.v) && (q < P.v);
-      double* row = wg + ((int64_t)p * P.v + q) * P.ldw + r0;
+      const int p = p0 + m / P.tq, qq = q0 + m % P.tq;
+      const bool row_ok = (m < P.rows_valid) && (p < P.v) && (qq < P.v);
+      double* row = wg + ((int64_t)p * P.v + qq) * P.ldw + r0;
+      if (row_ok) {
 #pragma unroll
-      for (int ni = 0; ni < kMaxNFrag; ++ni) {
-        if (ni < nfrag && row_ok) {
+        for (int ni = 0; ni < NFRAG; ++ni) {
           // C fragment columns 2*kq, 2*kq+1 of the MMA -> tile columns 8*ni + sigma(2kq), sigma(2kq+1)
           const int c0 = 8 * ni + kq, c1 = 8 * ni + kq + 4;
           if (r0 + c0 < P.v) row[c0] = acc[mi][ni][0];
@@ -230,6 +331,31 @@ w_contract_dmma_kernel(const __grid_constant__ CUtensorMap tmA_n,   // box (16, 
         }
       }
     }
+  }
+}
+
+// host-side dispatch on the column-fragment count
+typedef void (*GemmKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
+
+inline GemmKernelFn gemm_kernel_for(int nfrag) {
+  switch (nfrag) {
+    case 1: return w_contract_dmma_kernel<1>;
+    case 2: return w_contract_dmma_kernel<2>;
+    case 3: return w_contract_dmma_kernel<3>;
+    case 4: return w_contract_dmma_kernel<4>;
+    case 5: return w_contract_dmma_kernel<5>;
+    case 6: return w_contract_dmma_kernel<6>;
+    case 7: return w_contract_dmma_kernel<7>;
+    case 8: return w_contract_dmma_kernel<8>;
+    case 9: return w_contract_dmma_kernel<9>;
+    case 10: return w_contract_dmma_kernel<10>;
+    case 11: return w_contract_dmma_kernel<11>;
+    case 12: return w_contract_dmma_kernel<12>;
+    case 13: return w_contract_dmma_kernel<13>;
+    case 14: return w_contract_dmma_kernel<14>;
+    case 15: return w_contract_dmma_kernel<15>;
+    case 16: return w_contract_dmma_kernel<16>;
+    default: return nullptr;
   }
 }
 
