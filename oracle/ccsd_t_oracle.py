@@ -4,16 +4,15 @@ TEST INFRASTRUCTURE ONLY.  Nothing under ``mpqc_b200/`` may import this module: 
 ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs
 of ``bench.py`` use it, and only as the checker / the CPU arm, never as the product path.
 
-PARITY PINNING.  The reference holds no test that pins E(T) at the (tensors -> E(T))
-boundary: its only pin is the end-to-end validation case
-``tests/validation/reference/outputs/h2o-ccsd_t-631g-pvdz.out:395`` which needs Libint2,
-basis-set data, TiledArray and MADNESS, none of which exist in the build container, and the
-reference itself cannot be compiled here.  The three restatements below (straight, coarse,
-ijk-driven) are therefore pinned (i) against each other, (ii) against the plain-C literal
-restatement in ``oracle/ccsd_t_ref.c`` and (iii) -- see ``oracle/h2o_golden.py`` -- against the
-reference's stored H2O/6-31G value by an independent from-scratch integral+RHF+CCSD pipeline
-when that pipeline reproduces the stored SCF and CCSD energies.  Where (iii) is not met the
-status is "parity unpinned" and DESIGN.md says so.
+PARITY PINNING.  The reference holds no test that pins E(T) at the (tensors -> E(T)) boundary (SURVEY.md
+section 8c) and cannot be compiled here (TiledArray / MADNESS / Libint2 / Boost / TBB / Eigen / MPI absent); its only
+pin is the end-to-end validation case ``tests/validation/reference/outputs/h2o-ccsd_t-631g-pvdz.out:395``,
+(T) = -0.000868413807153793 Eh.  ``oracle/h2o_golden.py`` rebuilds that case from scratch (own Gaussian
+integrals, DF-RHF, spin-orbital DF-CCSD), reproduces the stored SCF (1e-12) and MP2 (2e-12) energies, and feeds the
+resulting tensors to the functions below: all three restatements return the reference's stored (T) to 4e-13 Eh
+(``tests/golden/h2o_631g.npz``, ``tests/test_oracle.py::test_h2o_reference_golden``).  STATUS: PINNED against a
+reference-produced number.  In addition the three restatements (straight, coarse, ijk-driven) are pinned against
+each other and against the plain-C literal restatement in ``oracle/ccsd_t_ref.c``.
 
 All citations are ``file:line`` in ``/root/reference/src/mpqc/chemistry/qc/lcao/cc/ccsd_t.h``
 unless another file is named.

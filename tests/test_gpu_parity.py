@@ -197,6 +197,20 @@ def test_v_only_and_w_only_linearity(lib):
     assert abs((e2 - e0) - 2.0 * (e1 - e0)) < TOL
 
 
+def test_h2o_reference_golden_value(lib):
+    # the reference's own stored (T) for H2O/6-31G (tests/validation/reference/outputs/h2o-ccsd_t-631g-pvdz.out:395)
+    # from the committed tensor fixture, through the plugin interface with its frozen core (o=4, v=8)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "h2o_631g.npz"))
+    cc = DenseCCSD(np.ascontiguousarray(g["t1"]), np.ascontiguousarray(g["t2"]), np.ascontiguousarray(g["g_abij"]),
+                   np.ascontiguousarray(g["g_aijk"]), np.ascontiguousarray(g["g_abci"]), g["eps"],
+                   n_frozen=int(g["n_frozen"]), e_ccsd=float(g["ref_scf"]) + float(g["ref_ccsd"]))
+    wfn = CCSD_T({"type": "CCSD(T)", "approach": "straight", "reblock_occ": 4, "reblock_unocc": 4}, ccsd=cc,
+                 out=io.StringIO())
+    res = wfn.evaluate(Energy())
+    assert abs(wfn.triples_energy() - (-0.000868413807153793)) < 1e-11        # north star: 1e-9
+    assert abs(res.value - (-76.346526406089026)) < 1e-9                       # check.py tolerance for Energy
+
+
 # ---------------------------------------------------------------------------------------------
 # BASELINE.json configs at full size (inputs generated in HBM): sampled units vs the oracle
 # ---------------------------------------------------------------------------------------------

@@ -111,3 +111,45 @@ def test_single_occupied_is_zero():
     p = make_problem(1, 4)
     assert abs(oc.straight(*_args(p))) < 1e-14
     assert oc.ijk_triple_list(1) == []
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the reference-produced pin: H2O / 6-31G / DF cc-pVDZ, tests/validation/reference/outputs/h2o-ccsd_t-631g-pvdz.out
+# ---------------------------------------------------------------------------------------------------------
+H2O = os.path.join(os.path.dirname(__file__), "golden", "h2o_631g.npz")
+REF_T = -0.000868413807153793      # outputs/h2o-ccsd_t-631g-pvdz.out:395
+
+
+def _h2o_args():
+    g = np.load(H2O)
+    nf, no = int(g["n_frozen"]), int(g["n_occ"])
+    eps = g["eps"]
+    return g, (g["t1"], g["t2"], g["g_abij"], g["g_aijk"], g["g_abci"], eps[nf:no].copy(), eps[no:].copy())
+
+
+def test_h2o_reference_golden():
+    g, args = _h2o_args()
+    assert float(g["ref_t"]) == REF_T
+    assert args[0].shape == (8, 4)                    # o = 4 (frozen core), v = 8 as in the reference log (:243-262)
+    for e in (oc.straight(*args), oc.coarse(*args, vir_block=8), oc.coarse(*args, vir_block=4),
+              oc.coarse(*args, vir_block=3), oc.ijk_driven(*args)):
+        assert abs(e - REF_T) < 1e-11, e               # observed 4.4e-13
+    eps_all = g["eps"]
+    e_c = straight_c(args[0], args[1], args[2], args[3], args[4], eps_all, int(g["n_frozen"]), 0)
+    assert abs(e_c - REF_T) < 1e-11
+    # the pipeline that produced the tensors reproduced the reference's SCF / MP2 / CCSD energies
+    assert abs(float(g["e_scf"]) - float(g["ref_scf"])) < 1e-10
+    assert abs(float(g["e_mp2"]) - float(g["ref_mp2"])) < 1e-10
+    assert abs(float(g["e_ccsd"]) - float(g["ref_ccsd"])) < 1e-9      # reference converged CCSD to 1e-9 (:313)
+
+
+def test_h2o_fixture_is_reproducible():
+    # regenerate the tensors from scratch (integrals -> DF-RHF -> DF-CCSD) and compare with the committed fixture
+    from oracle import h2o_golden
+    e_scf, cc, e_t = h2o_golden.main(write=False)
+    g, args = _h2o_args()
+    assert abs(e_scf - h2o_golden.REF["scf"]) < 1e-10
+    assert abs(cc["e_mp2"] - h2o_golden.REF["mp2"]) < 1e-10
+    assert abs(e_t["straight"] - REF_T) < 1e-11
+    # amplitudes are defined up to orbital phases, which E(T) is invariant to: compare invariants
+    assert abs(np.linalg.norm(cc["t2"]) - np.linalg.norm(args[1])) < 1e-9
