@@ -87,11 +87,12 @@ struct mpqc_t_handle {
   int num_sms = 0;
   cudaStream_t stream = nullptr;
   // resident operands
-  double *A = nullptr, *B = nullptr, *GV = nullptr, *T1T = nullptr, *eps_occ = nullptr, *eps_vir = nullptr;
+  double *A = nullptr, *AT = nullptr, *B = nullptr, *GV = nullptr, *T1T = nullptr, *eps_occ = nullptr, *eps_vir = nullptr;
   uint8_t* tile_sets = nullptr;
   bool uploaded = false;
   // plan
   int tp = 0, tq = 0, tn = 0, nfrag = 0, npt = 0, nqt = 0, nnt = 0, ldw = 0, kblocks = 0;
+  int flat = 0, nmt = 0;
   int ntile = 0, ntt = 0;
   CUtensorMap tmA_n, tmA_t, tmB;
   // work buffers
@@ -131,6 +132,7 @@ int plan(mpqc_t_handle* h) {
   }
   h->npt = (v + h->tp - 1) / h->tp;
   h->nqt = (v + h->tq - 1) / h->tq;
+  h->nmt = h->flat ? (int)(((int64_t)v * v + kBM - 1) / kBM) : h->npt * h->nqt;
   const int bn = kMaxNFrag * 8;
   h->nnt = (v + bn - 1) / bn;
   int cols = (v + h->nnt - 1) / h->nnt;
@@ -145,7 +147,13 @@ int plan(mpqc_t_handle* h) {
 
 int make_maps(mpqc_t_handle* h) {
   const uint64_t v = (uint64_t)h->v, o = (uint64_t)h->o, Kp = (uint64_t)h->Kp;
-  {
+  if (h->flat) {
+    uint64_t dims[3] = {Kp, v * v, o};
+    uint64_t str[2] = {Kp * 8, v * v * Kp * 8};
+    uint32_t box[3] = {(uint32_t)kBK, (uint32_t)kBM, 1};
+    MPQC_T_TRY(encode_map(&h->tmA_n, h->A, 3, dims, str, box));
+    MPQC_T_TRY(encode_map(&h->tmA_t, h->AT, 3, dims, str, box));
+  } else {
     uint64_t dims[4] = {Kp, v, v, o};
     uint64_t str[3] = {Kp * 8, v * Kp * 8, v * v * Kp * 8};
     uint32_t box_n[4] = {(uint32_t)kBK, (uint32_t)h->tq, (uint32_t)h->tp, 1};
@@ -186,7 +194,7 @@ int ensure_units(mpqc_t_handle* h, int64_t n) {
 }
 
 int auto_batch(const mpqc_t_handle* h) {
-  int64_t tiles_per_triple = 3LL * h->npt * h->nqt * h->nnt;
+  int64_t tiles_per_triple = 3LL * h->nmt * h->nnt;
   int64_t nb = (8LL * h->num_sms + tiles_per_triple - 1) / tiles_per_triple;
   nb = std::max<int64_t>(1, std::min<int64_t>(nb, 1024));
   // bound the W workspace to ~6 GB
@@ -220,10 +228,12 @@ GemmParams gemm_params(const mpqc_t_handle* h, int nbatch, const int* triples_de
   P.npt = h->npt;
   P.nqt = h->nqt;
   P.nnt = h->nnt;
-  P.tiles_per_group = h->npt * h->nqt * h->nnt;
+  P.flat = h->flat;
+  P.nmt = h->nmt;
+  P.tiles_per_group = h->nmt * h->nnt;
   P.total_tiles = nbatch * 3 * P.tiles_per_group;
   P.ldw = h->ldw;
-  P.rows_valid = h->tp * h->tq;
+  P.rows_valid = h->flat ? kBM : h->tp * h->tq;
   P.triples = triples_dev;
   P.w = h->W;
   return P;
@@ -288,6 +298,7 @@ int upload_impl(mpqc_t_handle* h, const mpqc_t_problem* p, bool on_device, mpqc_
   double t_copy = 0.0;
 
   MPQC_T_CUDA(cudaMemsetAsync(h->A, 0, (size_t)o * v * v * Kp * sizeof(double), st));
+  if (h->flat) MPQC_T_CUDA(cudaMemsetAsync(h->AT, 0, (size_t)o * v * v * Kp * sizeof(double), st));
   MPQC_T_CUDA(cudaMemsetAsync(h->B, 0, (size_t)o * o * v * Kp * sizeof(double), st));
 
   {
@@ -316,15 +327,19 @@ int upload_impl(mpqc_t_handle* h, const mpqc_t_problem* p, bool on_device, mpqc_
     // B particle part: t2[kap][r][(y,z)] -> B[(y,z)][r][kap]
     MPQC_T_TRY(launch_transpose(st, t2.ptr, h->B, v, v, o * o, 1, v * Kp, 0, Kp, &launches));
     // B hole part: g_aijk[r][(y,z)][l] -> B[(y,z)][r][v + l]
-    MPQC_T_TRY(launch_copy_hole(st, gaijk.ptr, h->B, v, o * o, o, Kp, v * Kp, v, 1.0, &launches));
-    // A hole part: -t2[(p,q)][x][l] -> A[x][(p,q)][v + l]
-    MPQC_T_TRY(launch_copy_hole(st, t2.ptr, h->A, v * v, o, o, Kp, v * v * Kp, v, -1.0, &launches));
+    MPQC_T_TRY(launch_copy_hole(st, gaijk.ptr, h->B, v, o * o, o, 1, Kp, 0, v * Kp, v, 1.0, &launches));
+    // A hole part: -t2[(p,q)][x][l] -> A[x][p][q][v + l]   (and AT[x][q][p][v + l])
+    MPQC_T_TRY(launch_copy_hole(st, t2.ptr, h->A, v * v, o, o, v, v * Kp, Kp, v * v * Kp, v, -1.0, &launches));
+    if (h->flat)
+      MPQC_T_TRY(launch_copy_hole(st, t2.ptr, h->AT, v * v, o, o, v, Kp, v * Kp, v * v * Kp, v, -1.0, &launches));
     MPQC_T_CUDA(cudaStreamSynchronize(st));  // staged buffers are freed on scope exit
   }
 
   // A particle part: g_abci[kap][p][(q,x)] -> A[x][p][q][kap], streamed in kap slabs
   if (on_device) {
     MPQC_T_TRY(launch_transpose(st, p->g_abci, h->A, v, v, v * o, o, Kp, v * v * Kp, v * Kp, &launches));
+    if (h->flat)   // AT[x][P][Q][d] = g_abci[d][Q][P][x]: mid (first virtual) -> Q, j / o (second virtual) -> P
+      MPQC_T_TRY(launch_transpose(st, p->g_abci, h->AT, v, v, v * o, o, v * Kp, v * v * Kp, Kp, &launches));
     MPQC_T_CUDA(cudaStreamSynchronize(st));
   } else {
     const size_t row = (size_t)v * v * o;  // doubles per kap
@@ -347,6 +362,8 @@ int upload_impl(mpqc_t_handle* h, const mpqc_t_problem* p, bool on_device, mpqc_
       t_copy += now_s() - tc;
       h2d += (int64_t)(nd * row * 8);
       rc = launch_transpose(st, buf[which], h->A + d0, nd, v, v * o, o, Kp, v * v * Kp, v * Kp, &launches);
+      if (rc == MPQC_T_OK && h->flat)
+        rc = launch_transpose(st, buf[which], h->AT + d0, nd, v, v * o, o, v * Kp, v * v * Kp, Kp, &launches);
       cudaEventRecord(done[which], st);
     }
     cudaStreamSynchronize(st);
@@ -429,7 +446,7 @@ int run_units(mpqc_t_handle* h, const std::vector<int>& all_triples, const int64
     stats->units += n;
     stats->kernel_launches += launches;
     stats->flops += (double)n * mpqc_t_unit_flops(h->o, h->v);
-    double mpad = (double)h->npt * h->nqt * kBM, npad = (double)h->nnt * h->tn;
+    double mpad = (double)h->nmt * kBM, npad = (double)h->nnt * h->tn;
     stats->flops_executed += (double)n * 3.0 * 2.0 * 2.0 * mpad * npad * (double)h->Kp;
     stats->bytes_d2h += n * 8;
     stats->bytes_h2d += n * 12;
@@ -535,7 +552,19 @@ int mpqc_t_create(mpqc_t_handle** out, int64_t o, int64_t v, int32_t device) {
   h->num_sms = prop.multiProcessorCount;
   int rc = [&]() -> int {
     MPQC_T_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    {
+      // "flat" mode keeps a transposed copy AT of the big operand so both GEMM terms read 128 consecutive
+      // flattened (p,q) rows (no row-patch padding).  Use it when 2|A| + the rest leaves >= 25% of free HBM.
+      size_t free_b = 0, total_b = 0;
+      MPQC_T_CUDA(cudaMemGetInfo(&free_b, &total_b));
+      const double a_bytes = (double)o * v * v * h->Kp * 8.0;
+      const double rest = (double)o * o * v * h->Kp * 8.0 + (double)o * o * v * v * 8.0 + 8e9;
+      const char* env = getenv("MPQC_T_FLAT");
+      h->flat = (2.0 * a_bytes + rest) < 0.75 * (double)free_b ? 1 : 0;
+      if (env) h->flat = atoi(env) != 0;
+    }
     MPQC_T_CUDA(cudaMalloc(&h->A, (size_t)o * v * v * h->Kp * sizeof(double)));
+    if (h->flat) MPQC_T_CUDA(cudaMalloc(&h->AT, (size_t)o * v * v * h->Kp * sizeof(double)));
     MPQC_T_CUDA(cudaMalloc(&h->B, (size_t)o * o * v * h->Kp * sizeof(double)));
     MPQC_T_CUDA(cudaMalloc(&h->GV, (size_t)o * o * v * v * sizeof(double)));
     MPQC_T_CUDA(cudaMalloc(&h->T1T, (size_t)o * v * sizeof(double)));
@@ -578,6 +607,7 @@ int mpqc_t_destroy(mpqc_t_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   free_work(h);
   cudaFree(h->A);
+  cudaFree(h->AT);
   cudaFree(h->B);
   cudaFree(h->GV);
   cudaFree(h->T1T);

@@ -7,6 +7,8 @@
 //                     kap >= v : -t2[p][q][x][kap-v]       (hole operand, t2_abil of :328-331, sign folded in)
 //   B[y][z][r][kap]   kap <  v : t2[kap][r][y][z]          (t2_dcjk of :316-319)
 //                     kap >= v : g_aijk[r][y][z][kap-v]    (g_cjkl of :321-326)
+//   AT[x][p][q][kap]  = A[x][q][p][kap]  (optional transposed copy: lets the second GEMM term read the same
+//                     flattened (p,q) row range as the first; built when 2|A| fits in HBM, "flat" mode)
 //   GV[i][j][a][b]    g_abij[a][b][i][j]                   (for the disconnected term, :379-409)
 //   T1T[i][a]         t1[a][i]
 // kap runs over Kp = roundup8(v+o) >= 16 (zero padded) so that particle and hole terms are ONE
@@ -41,17 +43,18 @@ transpose_kap_last_kernel(const double* __restrict__ in, double* __restrict__ ou
   }
 }
 
-// in[outer][mid][l] (l in [0,o))  ->  out[outer * so + mid * sm + koff + l] = scale * in
+// in[outer][mid][l] (l in [0,o))  ->  out[(outer / odiv) * so1 + (outer % odiv) * so2 + mid * sm + koff + l] = scale * in
 __global__ void __launch_bounds__(256)
 copy_hole_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t n_outer,
-                 int64_t n_mid, int64_t o, int64_t so, int64_t sm, int64_t koff, double scale) {
+                 int64_t n_mid, int64_t o, int64_t odiv, int64_t so1, int64_t so2, int64_t sm, int64_t koff,
+                 double scale) {
   const int64_t total = n_outer * n_mid * o;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     int64_t l = idx % o;
     int64_t mid = (idx / o) % n_mid;
     int64_t outer = idx / (o * n_mid);
-    out[outer * so + mid * sm + koff + l] = scale * __ldg(in + idx);
+    out[(outer / odiv) * so1 + (outer % odiv) * so2 + mid * sm + koff + l] = scale * __ldg(in + idx);
   }
 }
 
@@ -76,13 +79,13 @@ inline int launch_transpose(cudaStream_t st, const double* in, double* out, int6
 }
 
 inline int launch_copy_hole(cudaStream_t st, const double* in, double* out, int64_t n_outer,
-                            int64_t n_mid, int64_t o, int64_t so, int64_t sm, int64_t koff,
-                            double scale, int64_t* launches) {
+                            int64_t n_mid, int64_t o, int64_t odiv, int64_t so1, int64_t so2, int64_t sm,
+                            int64_t koff, double scale, int64_t* launches) {
   int64_t total = n_outer * n_mid * o;
   if (total == 0) return MPQC_T_OK;
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  copy_hole_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, out, n_outer, n_mid, o, so, sm, koff, scale);
+  copy_hole_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, out, n_outer, n_mid, o, odiv, so1, so2, sm, koff, scale);
   MPQC_T_CUDA(cudaGetLastError());
   if (launches) ++*launches;
   return MPQC_T_OK;

@@ -65,6 +65,10 @@ __device__ __forceinline__ void cp_async_16_zfill(uint32_t dst, const void* src,
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 
+__device__ __forceinline__ void cp_async_8_zfill(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
 __global__ void __launch_bounds__(kEThreads, 2)
 t_energy_fused_kernel(const EnergyParams P) {
   extern __shared__ __align__(16) uint8_t esmem[];
@@ -107,26 +111,35 @@ t_energy_fused_kernel(const EnergyParams P) {
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
 
-  // ---- small operands (L2 resident): g_ij / g_jk / g_ik patches, t1 and eps slices ----
-  for (int e = tid; e < 27 * 64; e += kEThreads) {
-    const int c = e & 7, r = (e >> 3) & 7, tcol = (e >> 6) % 3, trow = (e / 192) % 3, which = e / 576;
-    const int x = which == 1 ? j : i;
-    const int y = which == 0 ? j : k;
-    const int gr = (trow == 0 ? T[0] : (trow == 1 ? T[1] : T[2])) * kET + r;
-    const int gc = (tcol == 0 ? T[0] : (tcol == 1 ? T[1] : T[2])) * kET + c;
-    double val = 0.0;
-    if (gr < v && gc < v) val = __ldg(P.gv + ((int64_t)(x * P.o + y) * v + gr) * v + gc);
-    Gs[e] = val;
-  }
-  if (tid < 72) {
-    const int c = tid & 7, t = (tid >> 3) % 3, which = tid / 24;
-    const int x = which == 0 ? i : (which == 1 ? j : k);
-    const int gc = (t == 0 ? T[0] : (t == 1 ? T[1] : T[2])) * kET + c;
-    T1s[tid] = gc < v ? __ldg(P.t1t + (int64_t)x * v + gc) : 0.0;
-  } else if (tid >= 96 && tid < 120) {
-    const int c = tid & 7, t = (tid - 96) >> 3;
-    const int gc = (t == 0 ? T[0] : (t == 1 ? T[1] : T[2])) * kET + c;
-    Ev[tid - 96] = gc < v ? __ldg(P.eps_vir + gc) : 0.0;
+  // ---- small operands (L2 resident): g_ij / g_jk / g_ik patches, t1 and eps slices; also asynchronous so
+  //      that no load latency is serialised in front of the compute phase ----
+  {
+    const uint32_t g_base = smem_u32(Gs);
+#pragma unroll
+    for (int it = 0; it < 7; ++it) {
+      const int e = it * kEThreads + tid;
+      if (e < 27 * 64) {
+        const int c = e & 7, r = (e >> 3) & 7, tcol = (e >> 6) % 3, trow = (e / 192) % 3, which = e / 576;
+        const int x = which == 1 ? j : i;
+        const int y = which == 0 ? j : k;
+        const int gr = (trow == 0 ? T[0] : (trow == 1 ? T[1] : T[2])) * kET + r;
+        const int gc = (tcol == 0 ? T[0] : (tcol == 1 ? T[1] : T[2])) * kET + c;
+        const bool ok = gr < v && gc < v;
+        const double* src = P.gv + ((int64_t)(x * P.o + y) * v + (ok ? gr : 0)) * v + (ok ? gc : 0);
+        cp_async_8_zfill(g_base + (uint32_t)e * 8u, src, ok ? 8 : 0);
+      }
+    }
+    if (tid < 72) {
+      const int c = tid & 7, t = (tid >> 3) % 3, which = tid / 24;
+      const int x = which == 0 ? i : (which == 1 ? j : k);
+      const int gc = (t == 0 ? T[0] : (t == 1 ? T[1] : T[2])) * kET + c;
+      cp_async_8_zfill(smem_u32(T1s) + (uint32_t)tid * 8u, P.t1t + (int64_t)x * v + (gc < v ? gc : 0), gc < v ? 8 : 0);
+    } else if (tid >= 96 && tid < 120) {
+      const int c = tid & 7, t = (tid - 96) >> 3;
+      const int gc = (t == 0 ? T[0] : (t == 1 ? T[1] : T[2])) * kET + c;
+      cp_async_8_zfill(smem_u32(Ev) + (uint32_t)(tid - 96) * 8u, P.eps_vir + (gc < v ? gc : 0), gc < v ? 8 : 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
   const double eijk = __ldg(P.eps_occ + i) + __ldg(P.eps_occ + j) + __ldg(P.eps_occ + k);
 

@@ -25,8 +25,10 @@
 // separated by 6-8 independent ones; the half-filled last k-block (Kp % 16 == 8) is a separate
 // instantiation instead of predicated-off DMMAs.
 //
-// Tile rows are a (tp x tq) patch of (p,q); the second term reads the SAME rows from the
-// transposed patch A_x2[q][p][:] with a second TMA box, so no transposed copy of A exists.
+// Tile rows, two modes.  "flat" (default when 2|A| fits in HBM): 128 consecutive flattened (p,q) rows; the
+// second term reads the same row range from the transposed copy AT[x][p][q][:] = A[x][q][p][:], so there is
+// no row padding at all.  "patch" (large problems): rows are a (tp x tq) patch of (p,q) and the second term
+// reads the SAME rows from the transposed patch A_x2[q][p][:] with a second TMA box of the same memory.
 #pragma once
 
 #include "common.cuh"
@@ -46,9 +48,11 @@ constexpr int kGemmSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*ba
 
 struct GemmParams {
   int v, o, Kp, kblocks;      // kblocks = ceil(Kp / 16)
-  int tp, tq, tn, nfrag;      // row patch, column tile, tn = 8 * nfrag
-  int npt, nqt, nnt;          // tile counts along p, q, r
-  int tiles_per_group;        // npt * nqt * nnt
+  int tp, tq, tn, nfrag;      // row patch (patch mode), column tile, tn = 8 * nfrag
+  int npt, nqt, nnt;          // tile counts along p, q (patch mode), r
+  int flat;                   // 1: rows are 128 consecutive flattened (p,q) and term 1 reads the transposed copy AT
+  int nmt;                    // row tiles: ceil(v*v/128) (flat) or npt*nqt (patch)
+  int tiles_per_group;        // nmt * nnt
   int total_tiles;            // nbatch * 3 * tiles_per_group
   int ldw;                    // row pitch (doubles) of the N_g arrays
   int rows_valid;             // tp * tq
@@ -61,14 +65,11 @@ struct GemmParams {
 // 128B-swizzled tile (conflict-free LDS.128).
 __device__ __forceinline__ int sigma8(int g) { return (g >> 1) | ((g & 1) << 2); }
 
-__device__ __forceinline__ void decode_tile(const GemmParams& P, int tile, int& b, int& g, int& pt,
-                                            int& qt, int& nt) {
+__device__ __forceinline__ void decode_tile(const GemmParams& P, int tile, int& b, int& g, int& mt, int& nt) {
   nt = tile % P.nnt;
   int t = tile / P.nnt;
-  qt = t % P.nqt;
-  t /= P.nqt;
-  pt = t % P.npt;
-  t /= P.npt;
+  mt = t % P.nmt;
+  t /= P.nmt;
   g = t % 3;
   b = t / 3;
 }
@@ -178,8 +179,8 @@ __device__ __forceinline__ void kblock(double (&acc)[2][NFRAG][2], ConsumerRegs<
 
 template <int NFRAG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-w_contract_dmma_kernel(const __grid_constant__ CUtensorMap tmA_n,   // box (16, tq, tp, 1)
-                       const __grid_constant__ CUtensorMap tmA_t,   // box (16, tp, tq, 1)
+w_contract_dmma_kernel(const __grid_constant__ CUtensorMap tmA_n,   // patch: A box (16, tq, tp, 1) | flat: A  box (16, 128, 1)
+                       const __grid_constant__ CUtensorMap tmA_t,   // patch: A box (16, tp, tq, 1) | flat: AT box (16, 128, 1)
                        const __grid_constant__ CUtensorMap tmB,     // box (16, tn, 1)
                        const GemmParams P) {
   static_assert(NFRAG >= 1 && NFRAG <= kMaxNFrag, "NFRAG out of range");
@@ -216,14 +217,14 @@ w_contract_dmma_kernel(const __grid_constant__ CUtensorMap tmA_n,   // box (16, 
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        int b, g, pt, qt, nt;
-        decode_tile(P, tile, b, g, pt, qt, nt);
+        int b, g, mt, nt;
+        decode_tile(P, tile, b, g, mt, nt);
         const int i = P.triples[3 * b + 0], j = P.triples[3 * b + 1], k = P.triples[3 * b + 2];
         int x1, yz1, x2, yz2;
         if (g == 0)      { x1 = i; yz1 = j * P.o + k; x2 = j; yz2 = i * P.o + k; }
         else if (g == 1) { x1 = i; yz1 = k * P.o + j; x2 = k; yz2 = i * P.o + j; }
         else             { x1 = k; yz1 = j * P.o + i; x2 = j; yz2 = k * P.o + i; }
-        const int p0 = pt * P.tp, q0 = qt * P.tq, r0 = nt * P.tn;
+        const int p0 = (mt / P.nqt) * P.tp, q0 = (mt % P.nqt) * P.tq, r0 = nt * P.tn, m0 = mt * kBM;
         for (int term = 0; term < 2; ++term) {
           for (int kb = 0; kb < P.kblocks; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -231,10 +232,12 @@ w_contract_dmma_kernel(const __grid_constant__ CUtensorMap tmA_n,   // box (16, 
             uint8_t* sb = sa + kAStageBytes;
             mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
             if (term == 0) {
-              tma_load_4d(sa, &tmA_n, &full_bar[stage], kb * kBK, q0, p0, x1);
+              if (P.flat) tma_load_3d(sa, &tmA_n, &full_bar[stage], kb * kBK, m0, x1);
+              else        tma_load_4d(sa, &tmA_n, &full_bar[stage], kb * kBK, q0, p0, x1);
               tma_load_3d(sb, &tmB, &full_bar[stage], kb * kBK, r0, yz1);
             } else {
-              tma_load_4d(sa, &tmA_t, &full_bar[stage], kb * kBK, p0, q0, x2);
+              if (P.flat) tma_load_3d(sa, &tmA_t, &full_bar[stage], kb * kBK, m0, x2);
+              else        tma_load_4d(sa, &tmA_t, &full_bar[stage], kb * kBK, p0, q0, x2);
               tma_load_3d(sb, &tmB, &full_bar[stage], kb * kBK, r0, yz2);
             }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -262,7 +265,7 @@ w_contract_dmma_kernel(const __grid_constant__ CUtensorMap tmA_n,   // box (16, 
     int m = 16 * warp + 8 * mi + sg;
     a_off_n[mi] = (uint32_t)m * 128u + (uint32_t)((kq ^ (m & 7)) << 4);
     int mm = m < P.rows_valid ? m : 0;
-    int srow = (mm % P.tq) * P.tp + (mm / P.tq);     // row of (p,q) inside the transposed box
+    int srow = P.flat ? m : (mm % P.tq) * P.tp + (mm / P.tq);   // row of (p,q) inside the term-1 box
     a_off_t[mi] = (uint32_t)srow * 128u + (uint32_t)((kq ^ (srow & 7)) << 4);
   }
   const int kblocks = P.kblocks;
@@ -311,16 +314,24 @@ w_contract_dmma_kernel(const __grid_constant__ CUtensorMap tmA_n,   // box (16, 
     }
 
     // ---- epilogue: registers -> N_g[p][q][r0 + col] (32-byte sector-aligned runs) ----
-    int b, g, pt, qt, nt;
-    decode_tile(P, tile, b, g, pt, qt, nt);
-    const int p0 = pt * P.tp, q0 = qt * P.tq, r0 = nt * P.tn;
+    int b, g, mt, nt;
+    decode_tile(P, tile, b, g, mt, nt);
+    const int p0 = (mt / P.nqt) * P.tp, q0 = (mt % P.nqt) * P.tq, r0 = nt * P.tn;
     double* wg = P.w + ((int64_t)(b * 3 + g)) * P.v * P.v * P.ldw;
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi) {
       const int m = 16 * warp + 8 * mi + sg;
-      const int p = p0 + m / P.tq, qq = q0 + m % P.tq;
-      const bool row_ok = (m < P.rows_valid) && (p < P.v) && (qq < P.v);
-      double* row = wg + ((int64_t)p * P.v + qq) * P.ldw + r0;
+      int64_t pq;          // flattened p*v + q of this row
+      bool row_ok;
+      if (P.flat) {
+        pq = (int64_t)mt * kBM + m;
+        row_ok = pq < (int64_t)P.v * P.v;
+      } else {
+        const int p = p0 + m / P.tq, qq = q0 + m % P.tq;
+        pq = (int64_t)p * P.v + qq;
+        row_ok = (m < P.rows_valid) && (p < P.v) && (qq < P.v);
+      }
+      double* row = wg + pq * P.ldw + r0;
       if (row_ok) {
 #pragma unroll
         for (int ni = 0; ni < NFRAG; ++ni) {
