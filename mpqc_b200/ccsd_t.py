@@ -174,7 +174,7 @@ class CCSD_T:
     ``FeatureDisabled``.
 
     Extra keywords of the GPU path: ``ngpu`` (devices driven by this process), ``device_ids``,
-    ``batch``, and -- one-rank-per-GPU mode -- ``rank`` / ``world_size`` (unit sharding; the caller sums
+    ``batch``, ``use_nccl`` (sum the per-GPU partials with ncclAllReduce), and -- one-rank-per-GPU mode -- ``rank`` / ``world_size`` (unit sharding; the caller sums
     the partial energies with its own collective, replacing ``gop.sum`` at ccsd_t.h:692).
     """
 
@@ -203,6 +203,7 @@ class CCSD_T:
         self.ngpu_ = int(kv.get("ngpu", 1))
         self.device_ids_ = kv.get("device_ids")
         self.batch_ = int(kv.get("batch", 0))
+        self.use_nccl_ = bool(kv.get("use_nccl", False))
         self.rank_ = int(kv.get("rank", 0))
         self.world_size_ = int(kv.get("world_size", 1))
         if self.ngpu_ < 1:
@@ -276,6 +277,7 @@ class CCSD_T:
         opt.unit_stride = self.world_size_
         opt.unit_count = -1
         opt.batch = self.batch_
+        opt.use_nccl = 1 if self.use_nccl_ else 0
         st = L.Stats()
         e = C.c_double(0.0)
         lib = L.load()

@@ -15,6 +15,8 @@
 #include <thread>
 #include <vector>
 
+#include <dlfcn.h>
+
 #include "common.cuh"
 #include "microbench.cuh"
 #include "relayout.cuh"
@@ -75,6 +77,40 @@ int encode_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, con
 }
 
 int64_t roundup(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// ---- NCCL, bound at run time (dlopen) so the library has no link-time dependency and shares the NCCL that a
+//      host process (e.g. torch) may already have loaded.  Only the entry points the path needs: the final sum
+//      of the partial E(T) over NVLink (replaces gop.sum, ccsd_t.h:692). ----
+struct NcclApi {
+  typedef struct ncclComm* comm_t;
+  int (*CommInitAll)(comm_t*, int, const int*) = nullptr;
+  int (*CommDestroy)(comm_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+
+const NcclApi& nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* hnd = nullptr;
+    for (const char* n : names) {
+      hnd = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (hnd) break;
+    }
+    if (!hnd) return;
+    api.CommInitAll = reinterpret_cast<decltype(api.CommInitAll)>(dlsym(hnd, "ncclCommInitAll"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(hnd, "ncclCommDestroy"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(hnd, "ncclAllReduce"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(hnd, "ncclGetErrorString"));
+    api.ok = api.CommInitAll && api.CommDestroy && api.AllReduce;
+  });
+  return api;
+}
+constexpr int kNcclFloat64 = 8;   // ncclDouble
+constexpr int kNcclSum = 0;
 
 }  // namespace
 
@@ -714,6 +750,7 @@ int mpqc_t_energy(const mpqc_t_problem* p, const mpqc_t_options* opt_in, double*
   std::vector<int64_t> units((size_t)count);
   for (int64_t u = 0; u < count; ++u) units[u] = opt.unit_first + u * stride;
   std::vector<double> unit_e((size_t)count, 0.0);
+  std::vector<int> owner((size_t)count, -1);   // which GPU produced each unit (for the NCCL sum)
   std::vector<int> all;
   build_triple_list(p->o, all);
 
@@ -725,6 +762,20 @@ int mpqc_t_energy(const mpqc_t_problem* p, const mpqc_t_options* opt_in, double*
   const int64_t static_n = ngpu > 1 ? (count / 8) * 7 / ngpu * ngpu : count;
   tail_next.store(static_n);
   const bool profile = getenv("MPQC_T_PROFILE") != nullptr;
+
+  // optional NCCL sum: every GPU holds the per-unit energy vector (zeros for units it did not own); one
+  // ncclAllReduce(sum) over NVLink makes it complete everywhere (x + 0 + ... + 0 is exact, so the result is
+  // bit-identical to the host-side gather), then the units are summed in order.
+  const bool use_nccl = opt.use_nccl != 0 && ngpu > 1 && count > 0;
+  std::vector<NcclApi::comm_t> comms(ngpu, nullptr);
+  std::vector<double> nccl_result;
+  if (use_nccl) {
+    const NcclApi& nc = nccl_api();
+    MPQC_T_CHECK(nc.ok, MPQC_T_ERR_NCCL, "use_nccl requested but libnccl.so.2 could not be loaded");
+    int r = nc.CommInitAll(comms.data(), ngpu, devs.data());
+    if (r != 0) return fail(MPQC_T_ERR_NCCL, nc.GetErrorString ? nc.GetErrorString(r) : "ncclCommInitAll failed", __FILE__, __LINE__);
+    nccl_result.assign((size_t)count, 0.0);
+  }
 
   auto worker = [&](int g) {
     mpqc_t_stats& gs = gstats[g];
@@ -741,7 +792,10 @@ int mpqc_t_energy(const mpqc_t_problem* p, const mpqc_t_options* opt_in, double*
       for (size_t q = 0; q < mine.size(); ++q) idx[q] = units[mine[q]];
       rc = run_units(h, all, idx.data(), (int64_t)idx.size(), opt.batch, e.data(), &gs, profile);
       if (rc == MPQC_T_OK)
-        for (size_t q = 0; q < mine.size(); ++q) unit_e[mine[q]] = e[q];
+        for (size_t q = 0; q < mine.size(); ++q) {
+          unit_e[mine[q]] = e[q];
+          owner[mine[q]] = g;
+        }
       // work-stealing tail
       int64_t chunk = opt.steal_chunk > 0 ? opt.steal_chunk : std::max<int64_t>(1, auto_batch(h)) * 4;
       while (rc == MPQC_T_OK) {
@@ -751,8 +805,39 @@ int mpqc_t_energy(const mpqc_t_problem* p, const mpqc_t_options* opt_in, double*
         std::vector<double> e2((size_t)n);
         rc = run_units(h, all, units.data() + s, n, opt.batch, e2.data(), &gs, profile);
         if (rc == MPQC_T_OK)
-          for (int64_t q = 0; q < n; ++q) unit_e[s + q] = e2[q];
+          for (int64_t q = 0; q < n; ++q) {
+            unit_e[s + q] = e2[q];
+            owner[s + q] = g;
+          }
       }
+    }
+    if (use_nccl) {
+      // every thread must reach the collective, also after a failure (contribute zeros)
+      const NcclApi& nc = nccl_api();
+      cudaSetDevice(devs[g]);
+      double* dbuf = nullptr;
+      cudaStream_t st = nullptr;
+      int r2 = MPQC_T_OK;
+      if (cudaMalloc(&dbuf, (size_t)count * sizeof(double)) != cudaSuccess || cudaStreamCreate(&st) != cudaSuccess) {
+        r2 = fail(MPQC_T_ERR_OOM, "allocation for the NCCL sum failed", __FILE__, __LINE__);
+      } else {
+        std::vector<double> mine((size_t)count, 0.0);
+        if (rc == MPQC_T_OK) {
+          // this thread's contributions: unit_e holds every thread's results, so mask by ownership
+          for (int64_t u = 0; u < count; ++u)
+            if (owner[u] == g) mine[u] = unit_e[u];
+        }
+        cudaMemcpyAsync(dbuf, mine.data(), (size_t)count * sizeof(double), cudaMemcpyHostToDevice, st);
+        int r = nc.AllReduce(dbuf, dbuf, (size_t)count, kNcclFloat64, kNcclSum, comms[g], st);
+        if (r != 0) r2 = fail(MPQC_T_ERR_NCCL, nc.GetErrorString ? nc.GetErrorString(r) : "ncclAllReduce failed", __FILE__, __LINE__);
+        if (g == 0 && r2 == MPQC_T_OK)
+          cudaMemcpyAsync(nccl_result.data(), dbuf, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess && r2 == MPQC_T_OK)
+          r2 = fail(MPQC_T_ERR_CUDA, "stream sync after ncclAllReduce failed", __FILE__, __LINE__);
+      }
+      cudaFree(dbuf);
+      if (st) cudaStreamDestroy(st);
+      if (rc == MPQC_T_OK) rc = r2;
     }
     if (rc != MPQC_T_OK) msgs[g] = last_error_string();
     mpqc_t_destroy(h);
@@ -766,13 +851,22 @@ int mpqc_t_energy(const mpqc_t_problem* p, const mpqc_t_options* opt_in, double*
     for (int g = 0; g < ngpu; ++g) th.emplace_back(worker, g);
     for (auto& t : th) t.join();   // joined before returning (SURVEY 8b threading contract)
   }
+  if (use_nccl) {
+    const NcclApi& nc = nccl_api();
+    for (int g = 0; g < ngpu; ++g)
+      if (comms[g]) nc.CommDestroy(comms[g]);
+  }
   for (int g = 0; g < ngpu; ++g)
     if (rcs[g] != MPQC_T_OK) {
       last_error_string() = msgs[g];
       return rcs[g];
     }
   double e = 0.0;
-  for (int64_t u = 0; u < count; ++u) e += unit_e[u];
+  if (use_nccl) {
+    for (int64_t u = 0; u < count; ++u) e += nccl_result[u];   // the NCCL-summed vector, in unit order
+  } else {
+    for (int64_t u = 0; u < count; ++u) e += unit_e[u];
+  }
   *e_t = e;
 
   for (int g = 0; g < ngpu; ++g) {

@@ -197,6 +197,21 @@ def test_v_only_and_w_only_linearity(lib):
     assert abs((e2 - e0) - 2.0 * (e1 - e0)) < TOL
 
 
+@pytest.mark.parametrize("use_nccl", [0, 1])
+def test_in_process_multi_gpu_matches_single(lib, use_nccl):
+    # one process driving several GPUs: static + work-stealing split, partials summed on the host (0) or by one
+    # ncclAllReduce over NVLink (1); both must be bit-identical to the single-GPU result
+    ndev = lib.mpqc_t_device_count()
+    if ndev < 2:
+        pytest.skip("needs >= 2 GPUs")
+    p = make_problem(9, 40, seed=7)
+    e1, st1 = _energy_oneshot(lib, p)
+    e2, st2 = _energy_oneshot(lib, p, ngpu=min(ndev, 4), use_nccl=use_nccl, steal_chunk=5)
+    assert st2.ngpu == min(ndev, 4) and st2.units == st1.units
+    assert e2 == e1
+    assert abs(e1 - oc.ijk_driven(*_args(p))) < TOL
+
+
 def test_h2o_reference_golden_value(lib):
     # the reference's own stored (T) for H2O/6-31G (tests/validation/reference/outputs/h2o-ccsd_t-631g-pvdz.out:395)
     # from the committed tensor fixture, through the plugin interface with its frozen core (o=4, v=8)
