@@ -128,7 +128,7 @@ struct mpqc_t_handle {
   bool uploaded = false;
   // plan
   int tp = 0, tq = 0, tn = 0, nfrag = 0, npt = 0, nqt = 0, nnt = 0, ldw = 0, kblocks = 0;
-  int flat = 0, nmt = 0;
+  int flat = 0, nmt = 0, skip_last = 0;
   int ntile = 0, ntt = 0;
   CUtensorMap tmA_n, tmA_t, tmB;
   // work buffers
@@ -169,11 +169,12 @@ int plan(mpqc_t_handle* h) {
   h->npt = (v + h->tp - 1) / h->tp;
   h->nqt = (v + h->tq - 1) / h->tq;
   h->nmt = h->flat ? (int)(((int64_t)v * v + kBM - 1) / kBM) : h->npt * h->nqt;
-  const int bn = kMaxNFrag * 8;
-  h->nnt = (v + bn - 1) / bn;
-  int cols = (v + h->nnt - 1) / h->nnt;
-  h->nfrag = (cols + 7) / 8;
+  // column tiles: F = ceil(v/8) fragments over nnt tiles of NFRAG fragments; the last tile may drop one
+  const int F = (v + 7) / 8;
+  h->nnt = (F + kMaxNFrag - 1) / kMaxNFrag;
+  h->nfrag = (F + h->nnt - 1) / h->nnt;
   h->tn = h->nfrag * 8;
+  h->skip_last = (h->nfrag >= 2 && h->nnt * h->nfrag - 1 >= F) ? 1 : 0;
   h->ldw = (int)roundup(v, 16);
   h->kblocks = (int)((h->Kp + kBK - 1) / kBK);
   h->ntile = (v + kET - 1) / kET;
@@ -265,9 +266,11 @@ GemmParams gemm_params(const mpqc_t_handle* h, int nbatch, const int* triples_de
   P.nqt = h->nqt;
   P.nnt = h->nnt;
   P.flat = h->flat;
+  P.skip_last = h->skip_last;
   P.nmt = h->nmt;
   P.tiles_per_group = h->nmt * h->nnt;
   P.total_tiles = nbatch * 3 * P.tiles_per_group;
+  P.main_tiles = nbatch * 3 * h->nmt * (h->nnt - h->skip_last);
   P.ldw = h->ldw;
   P.rows_valid = h->flat ? kBM : h->tp * h->tq;
   P.triples = triples_dev;
@@ -482,7 +485,7 @@ int run_units(mpqc_t_handle* h, const std::vector<int>& all_triples, const int64
     stats->units += n;
     stats->kernel_launches += launches;
     stats->flops += (double)n * mpqc_t_unit_flops(h->o, h->v);
-    double mpad = (double)h->nmt * kBM, npad = (double)h->nnt * h->tn;
+    double mpad = (double)h->nmt * kBM, npad = (double)h->nnt * h->tn - 8.0 * h->skip_last;
     stats->flops_executed += (double)n * 3.0 * 2.0 * 2.0 * mpad * npad * (double)h->Kp;
     stats->bytes_d2h += n * 8;
     stats->bytes_h2d += n * 12;

@@ -162,12 +162,14 @@ t_energy_fused_kernel(const EnergyParams P) {
                 S[(1 * 6 + pi) * kETileElems + sw_idx(l[s0], l[s2], l[s1])] +
                 S[(2 * 6 + pi) * kETileElems + sw_idx(l[s2], l[s1], l[s0])];
       }
+      // Z_s = 4W_s + (two cyclic partners) - 2 (three transposed partners) = 3 W_s + S_same - 2 S_other, where
+      // S_even = W[abc]+W[bca]+W[cab] (perms 0,1,2) and S_odd = W[cba]+W[acb]+W[bac] (perms 3,4,5)
+      const double s_even = w[0] + w[1] + w[2], s_odd = w[3] + w[4] + w[5];
       double acc = 0.0;
 #pragma unroll
       for (int pi = 0; pi < 6; ++pi) {
         const int s0 = PERM[pi][0], s1 = PERM[pi][1], s2 = PERM[pi][2];
-        const double z = 4.0 * w[pi] + w[perm_index(s1, s2)] + w[perm_index(s2, s0)] -
-                         2.0 * (w[perm_index(s2, s1)] + w[perm_index(s0, s2)] + w[perm_index(s1, s0)]);
+        const double z = 3.0 * w[pi] + (pi < 3 ? s_even - 2.0 * s_odd : s_odd - 2.0 * s_even);
         // V for (a',b',c') = (e[s0], e[s1], e[s2]):  g_ij[a',b'] t1[c',k] + g_jk[b',c'] t1[a',i] + g_ik[a',c'] t1[b',j]
         const double vv = Gs[((0 * 3 + s0) * 3 + s1) * 64 + l[s0] * 8 + l[s1]] * T1s[(2 * 3 + s2) * 8 + l[s2]] +
                           Gs[((1 * 3 + s1) * 3 + s2) * 64 + l[s1] * 8 + l[s2]] * T1s[(0 * 3 + s0) * 8 + l[s0]] +

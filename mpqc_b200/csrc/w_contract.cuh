@@ -50,10 +50,12 @@ struct GemmParams {
   int v, o, Kp, kblocks;      // kblocks = ceil(Kp / 16)
   int tp, tq, tn, nfrag;      // row patch (patch mode), column tile, tn = 8 * nfrag
   int npt, nqt, nnt;          // tile counts along p, q (patch mode), r
+  int skip_last;              // 1: the last column tile drops its trailing fragment (tn*nnt - 8 >= v)
   int flat;                   // 1: rows are 128 consecutive flattened (p,q) and term 1 reads the transposed copy AT
   int nmt;                    // row tiles: ceil(v*v/128) (flat) or npt*nqt (patch)
   int tiles_per_group;        // nmt * nnt
   int total_tiles;            // nbatch * 3 * tiles_per_group
+  int main_tiles;             // tiles computing all NFRAG fragments; the remaining ones drop the last fragment
   int ldw;                    // row pitch (doubles) of the N_g arrays
   int rows_valid;             // tp * tq
   const int* triples;         // [nbatch][3] (i,j,k) of this launch
@@ -65,9 +67,19 @@ struct GemmParams {
 // 128B-swizzled tile (conflict-free LDS.128).
 __device__ __forceinline__ int sigma8(int g) { return (g >> 1) | ((g & 1) << 2); }
 
+// Tile order: first every "main" tile (column tiles that compute all NFRAG fragments), then the "skip" tiles
+// (the last column tile of each row of tiles when it drops its trailing fragment), so that a CTA walking
+// tile, tile + grid, ... runs one instantiation of the k-loop, then the other, and the short tiles fill the tail.
 __device__ __forceinline__ void decode_tile(const GemmParams& P, int tile, int& b, int& g, int& mt, int& nt) {
-  nt = tile % P.nnt;
-  int t = tile / P.nnt;
+  int t;
+  if (tile < P.main_tiles) {
+    const int nn = P.nnt - P.skip_last;
+    nt = tile % nn;
+    t = tile / nn;
+  } else {
+    nt = P.nnt - 1;
+    t = tile - P.main_tiles;
+  }
   mt = t % P.nmt;
   t /= P.nmt;
   g = t % 3;
@@ -98,11 +110,14 @@ __device__ __forceinline__ void load_b_chunk(BFrag (&b)[Chunking<NFRAG>::kMax], 
   }
 }
 
-template <int NFRAG, int C, bool HALF>
+// SKIP (0/1): number of trailing column fragments of the LAST chunk that this tile does not compute (the last
+// column tile of a row of tiles when 8*NFRAG*nnt overshoots v by a whole fragment); compile-time, so no
+// predicated DMMAs.
+template <int NFRAG, int C, bool HALF, int SKIP>
 __device__ __forceinline__ void mma_chunk(double (&acc)[2][NFRAG][2], const double2 (&alo)[2], const double2 (&ahi)[2],
                                           const BFrag (&b)[Chunking<NFRAG>::kMax]) {
   using CH = Chunking<NFRAG>;
-  constexpr int n0 = CH::beg(C), nl = CH::len(C);
+  constexpr int n0 = CH::beg(C), nl = CH::len(C) - ((C == CH::kNum - 1) ? SKIP : 0);
   // k-step major: consecutive DMMAs touch different accumulators
 #pragma unroll
   for (int u = 0; u < nl; ++u)
@@ -133,7 +148,7 @@ struct ConsumerRegs {
 
 // One k-block.  On entry R holds the A fragments and B chunk 0 (in bb[0]) of this block.  On exit, if
 // has_next, it holds those of the next block (read from stage `ns` after waiting on its full barrier).
-template <int NFRAG, bool HALF>
+template <int NFRAG, bool HALF, int SKIP>
 __device__ __forceinline__ void kblock(double (&acc)[2][NFRAG][2], ConsumerRegs<NFRAG>& R, uint32_t sb_cur,
                                        bool has_next, uint64_t* next_full, uint32_t next_phase, uint32_t sa_next,
                                        uint32_t a0_next, uint32_t a1_next, uint32_t sb_next) {
@@ -157,12 +172,12 @@ __device__ __forceinline__ void kblock(double (&acc)[2][NFRAG][2], ConsumerRegs<
       nhi[1] = lds128(sa_next + (a1_next ^ 64u));
       load_b_chunk<NFRAG, 0>(R.bb[(c + 1) & 1], sb_next);
     }
-    if (c == 0) mma_chunk<NFRAG, 0, HALF>(acc, R.alo, R.ahi, R.bb[0]);
-    if (c == 1) mma_chunk<NFRAG, (1 < CH::kNum ? 1 : 0), HALF>(acc, R.alo, R.ahi, R.bb[1]);
-    if (c == 2) mma_chunk<NFRAG, (2 < CH::kNum ? 2 : 0), HALF>(acc, R.alo, R.ahi, R.bb[0]);
-    if (c == 3) mma_chunk<NFRAG, (3 < CH::kNum ? 3 : 0), HALF>(acc, R.alo, R.ahi, R.bb[1]);
-    if (c == 4) mma_chunk<NFRAG, (4 < CH::kNum ? 4 : 0), HALF>(acc, R.alo, R.ahi, R.bb[0]);
-    if (c == 5) mma_chunk<NFRAG, (5 < CH::kNum ? 5 : 0), HALF>(acc, R.alo, R.ahi, R.bb[1]);
+    if (c == 0) mma_chunk<NFRAG, 0, HALF, SKIP>(acc, R.alo, R.ahi, R.bb[0]);
+    if (c == 1) mma_chunk<NFRAG, (1 < CH::kNum ? 1 : 0), HALF, SKIP>(acc, R.alo, R.ahi, R.bb[1]);
+    if (c == 2) mma_chunk<NFRAG, (2 < CH::kNum ? 2 : 0), HALF, SKIP>(acc, R.alo, R.ahi, R.bb[0]);
+    if (c == 3) mma_chunk<NFRAG, (3 < CH::kNum ? 3 : 0), HALF, SKIP>(acc, R.alo, R.ahi, R.bb[1]);
+    if (c == 4) mma_chunk<NFRAG, (4 < CH::kNum ? 4 : 0), HALF, SKIP>(acc, R.alo, R.ahi, R.bb[0]);
+    if (c == 5) mma_chunk<NFRAG, (5 < CH::kNum ? 5 : 0), HALF, SKIP>(acc, R.alo, R.ahi, R.bb[1]);
   }
   if (has_next) {
 #pragma unroll
@@ -173,6 +188,77 @@ __device__ __forceinline__ void kblock(double (&acc)[2][NFRAG][2], ConsumerRegs<
     if (CH::kNum & 1) {   // chunk 0 of the next block was loaded into bb[1]; the next block expects bb[0]
 #pragma unroll
       for (int u = 0; u < CH::kMax; ++u) R.bb[0][u] = R.bb[1][u];
+    }
+  }
+}
+
+// Consumer tile loop for tiles [tile, tile_end) of this CTA (stride gridDim.x); SKIP as in mma_chunk.
+template <int NFRAG, int SKIP>
+__device__ __forceinline__ void consume_tiles(const GemmParams& P, int& tile, const int tile_end, ConsumerRegs<NFRAG>& R,
+                                              int& stage, uint32_t& phase, uint64_t* full_bar, uint64_t* empty_bar,
+                                              const uint32_t smem_base, const uint32_t b_lo_off,
+                                              const uint32_t (&a_off_n)[2], const uint32_t (&a_off_t)[2], const int warp,
+                                              const int lane, const int sg, const int kq) {
+  const int kblocks = P.kblocks;
+  const int nblk = 2 * kblocks;                       // k-blocks per tile (two terms)
+  const bool half_last = (P.Kp % kBK) != 0;            // Kp % 16 == 8: last block of a term is half filled
+  for (; tile < tile_end; tile += gridDim.x) {
+    double acc[2][NFRAG][2];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < NFRAG; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    const bool more_tiles = tile + (int)gridDim.x < P.total_tiles;
+
+    for (int q = 0; q < nblk; ++q) {
+      const bool last_in_tile = (q == nblk - 1);
+      const bool has_next = !last_in_tile || more_tiles;
+      const bool next_transposed = !last_in_tile && (q + 1 >= kblocks);
+      const int ns = (stage + 1 == kStages) ? 0 : stage + 1;
+      const uint32_t nph = (ns == 0) ? (phase ^ 1u) : phase;
+      const uint32_t sa_next = smem_base + ns * kStageBytes;
+      const uint32_t a0n = next_transposed ? a_off_t[0] : a_off_n[0];
+      const uint32_t a1n = next_transposed ? a_off_t[1] : a_off_n[1];
+      const uint32_t sb_cur = smem_base + stage * kStageBytes + b_lo_off;
+      const bool half = half_last && (q == kblocks - 1 || q == nblk - 1);
+      if (half)
+        kblock<NFRAG, true, SKIP>(acc, R, sb_cur, has_next, &full_bar[ns], nph, sa_next, a0n, a1n, sa_next + b_lo_off);
+      else
+        kblock<NFRAG, false, SKIP>(acc, R, sb_cur, has_next, &full_bar[ns], nph, sa_next, a0n, a1n, sa_next + b_lo_off);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      stage = ns;
+      phase = nph;
+    }
+
+    // ---- epilogue: registers -> N_g[p][q][r0 + col] (32-byte sector-aligned runs) ----
+    int b, g, mt, nt;
+    decode_tile(P, tile, b, g, mt, nt);
+    const int p0 = (mt / P.nqt) * P.tp, q0 = (mt % P.nqt) * P.tq, r0 = nt * P.tn;
+    double* wg = P.w + ((int64_t)(b * 3 + g)) * P.v * P.v * P.ldw;
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+      const int m = 16 * warp + 8 * mi + sg;
+      int64_t pq;          // flattened p*v + q of this row
+      bool row_ok;
+      if (P.flat) {
+        pq = (int64_t)mt * kBM + m;
+        row_ok = pq < (int64_t)P.v * P.v;
+      } else {
+        const int p = p0 + m / P.tq, qq = q0 + m % P.tq;
+        pq = (int64_t)p * P.v + qq;
+        row_ok = (m < P.rows_valid) && (p < P.v) && (qq < P.v);
+      }
+      double* row = wg + pq * P.ldw + r0;
+      if (row_ok) {
+#pragma unroll
+        for (int ni = 0; ni < NFRAG - SKIP; ++ni) {
+          // C fragment columns 2*kq, 2*kq+1 of the MMA -> tile columns 8*ni + sigma(2kq), sigma(2kq+1)
+          const int c0 = 8 * ni + kq, c1 = 8 * ni + kq + 4;
+          if (r0 + c0 < P.v) row[c0] = acc[mi][ni][0];
+          if (r0 + c1 < P.v) row[c1] = acc[mi][ni][1];
+        }
+      }
     }
   }
 }
@@ -268,10 +354,6 @@ w_contract_dmma_kernel(const __grid_constant__ CUtensorMap tmA_n,   // patch: A 
     int srow = P.flat ? m : (mm % P.tq) * P.tp + (mm / P.tq);   // row of (p,q) inside the term-1 box
     a_off_t[mi] = (uint32_t)srow * 128u + (uint32_t)((kq ^ (srow & 7)) << 4);
   }
-  const int kblocks = P.kblocks;
-  const int nblk = 2 * kblocks;                       // k-blocks per tile (two terms)
-  const bool half_last = (P.Kp % kBK) != 0;            // Kp % 16 == 8: last block of a term is half filled
-
   int stage = 0;
   uint32_t phase = 0;
   ConsumerRegs<NFRAG> R;
@@ -284,65 +366,11 @@ w_contract_dmma_kernel(const __grid_constant__ CUtensorMap tmA_n,   // patch: A 
     R.ahi[1] = lds128(smem_base + (a_off_n[1] ^ 64u));
     load_b_chunk<NFRAG, 0>(R.bb[0], smem_base + b_lo_off);
   }
-  for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-    double acc[2][NFRAG][2];
-#pragma unroll
-    for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-      for (int ni = 0; ni < NFRAG; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-    const bool more_tiles = tile + (int)gridDim.x < P.total_tiles;
-
-    for (int q = 0; q < nblk; ++q) {
-      const bool last_in_tile = (q == nblk - 1);
-      const bool has_next = !last_in_tile || more_tiles;
-      const bool next_transposed = !last_in_tile && (q + 1 >= kblocks);
-      const int ns = (stage + 1 == kStages) ? 0 : stage + 1;
-      const uint32_t nph = (ns == 0) ? (phase ^ 1u) : phase;
-      const uint32_t sa_next = smem_base + ns * kStageBytes;
-      const uint32_t a0n = next_transposed ? a_off_t[0] : a_off_n[0];
-      const uint32_t a1n = next_transposed ? a_off_t[1] : a_off_n[1];
-      const uint32_t sb_cur = smem_base + stage * kStageBytes + b_lo_off;
-      const bool half = half_last && (q == kblocks - 1 || q == nblk - 1);
-      if (half)
-        kblock<NFRAG, true>(acc, R, sb_cur, has_next, &full_bar[ns], nph, sa_next, a0n, a1n, sa_next + b_lo_off);
-      else
-        kblock<NFRAG, false>(acc, R, sb_cur, has_next, &full_bar[ns], nph, sa_next, a0n, a1n, sa_next + b_lo_off);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[stage]);
-      stage = ns;
-      phase = nph;
-    }
-
-    // ---- epilogue: registers -> N_g[p][q][r0 + col] (32-byte sector-aligned runs) ----
-    int b, g, mt, nt;
-    decode_tile(P, tile, b, g, mt, nt);
-    const int p0 = (mt / P.nqt) * P.tp, q0 = (mt % P.nqt) * P.tq, r0 = nt * P.tn;
-    double* wg = P.w + ((int64_t)(b * 3 + g)) * P.v * P.v * P.ldw;
-#pragma unroll
-    for (int mi = 0; mi < 2; ++mi) {
-      const int m = 16 * warp + 8 * mi + sg;
-      int64_t pq;          // flattened p*v + q of this row
-      bool row_ok;
-      if (P.flat) {
-        pq = (int64_t)mt * kBM + m;
-        row_ok = pq < (int64_t)P.v * P.v;
-      } else {
-        const int p = p0 + m / P.tq, qq = q0 + m % P.tq;
-        pq = (int64_t)p * P.v + qq;
-        row_ok = (m < P.rows_valid) && (p < P.v) && (qq < P.v);
-      }
-      double* row = wg + pq * P.ldw + r0;
-      if (row_ok) {
-#pragma unroll
-        for (int ni = 0; ni < NFRAG; ++ni) {
-          // C fragment columns 2*kq, 2*kq+1 of the MMA -> tile columns 8*ni + sigma(2kq), sigma(2kq+1)
-          const int c0 = 8 * ni + kq, c1 = 8 * ni + kq + 4;
-          if (r0 + c0 < P.v) row[c0] = acc[mi][ni][0];
-          if (r0 + c1 < P.v) row[c1] = acc[mi][ni][1];
-        }
-      }
-    }
-  }
+  int tile = blockIdx.x;
+  consume_tiles<NFRAG, 0>(P, tile, P.main_tiles, R, stage, phase, full_bar, empty_bar, smem_base, b_lo_off, a_off_n,
+                          a_off_t, warp, lane, sg, kq);
+  consume_tiles<NFRAG, (NFRAG >= 2 ? 1 : 0)>(P, tile, P.total_tiles, R, stage, phase, full_bar, empty_bar, smem_base,
+                                            b_lo_off, a_off_n, a_off_t, warp, lane, sg, kq);
 }
 
 // host-side dispatch on the column-fragment count
