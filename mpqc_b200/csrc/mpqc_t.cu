@@ -232,7 +232,8 @@ int ensure_units(mpqc_t_handle* h, int64_t n) {
 
 int auto_batch(const mpqc_t_handle* h) {
   int64_t tiles_per_triple = 3LL * h->nmt * h->nnt;
-  int64_t nb = (8LL * h->num_sms + tiles_per_triple - 1) / tiles_per_triple;
+  // >= 64 waves of tiles per launch keeps the persistent grid's tail (half a tile per SM) under ~1%
+  int64_t nb = (64LL * h->num_sms + tiles_per_triple - 1) / tiles_per_triple;
   nb = std::max<int64_t>(1, std::min<int64_t>(nb, 1024));
   // bound the W workspace to ~6 GB
   size_t per = (size_t)3 * h->v * h->v * h->ldw * sizeof(double);
