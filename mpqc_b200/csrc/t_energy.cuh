@@ -28,7 +28,9 @@ constexpr int kET = 8;              // energy tile edge
 constexpr int kEThreads = 256;
 constexpr int kETileElems = kET * kET * kET;                 // 512 doubles
 constexpr int kEStageBytes = 18 * kETileElems * 8;           // 73,728 B of raw tiles
-constexpr int kESmallDoubles = 27 * 64 + 72 + 24 + 8;        // g patches, t1 slices, eps slices, reduction
+constexpr int kEGPitch = 9;                                  // padded row pitch of the 8x8 g patches (bank conflicts)
+constexpr int kEGPatch = 8 * kEGPitch;                       // doubles per patch
+constexpr int kESmallDoubles = 27 * kEGPatch + 72 + 24 + 8;  // g patches, t1 slices, eps slices, reduction
 constexpr int kEnergySmemBytes = kEStageBytes + kESmallDoubles * 8;
 
 struct EnergyParams {
@@ -74,7 +76,7 @@ t_energy_fused_kernel(const EnergyParams P) {
   extern __shared__ __align__(16) uint8_t esmem[];
   double* S = reinterpret_cast<double*>(esmem);                 // [3 arrays][6 perms][512] swizzled
   double* Gs = S + 18 * kETileElems;                            // [3][3][3][8][8]
-  double* T1s = Gs + 27 * 64;                                   // [3][3][8]
+  double* T1s = Gs + 27 * kEGPatch;                             // [3][3][8]
   double* Ev = T1s + 72;                                        // [3][8]
   double* red = Ev + 24;                                        // [8]
 
@@ -126,7 +128,7 @@ t_energy_fused_kernel(const EnergyParams P) {
         const int gc = (tcol == 0 ? T[0] : (tcol == 1 ? T[1] : T[2])) * kET + c;
         const bool ok = gr < v && gc < v;
         const double* src = P.gv + ((int64_t)(x * P.o + y) * v + (ok ? gr : 0)) * v + (ok ? gc : 0);
-        cp_async_8_zfill(g_base + (uint32_t)e * 8u, src, ok ? 8 : 0);
+        cp_async_8_zfill(g_base + (uint32_t)((e >> 6) * kEGPatch + r * kEGPitch + c) * 8u, src, ok ? 8 : 0);
       }
     }
     if (tid < 72) {
@@ -153,14 +155,17 @@ t_energy_fused_kernel(const EnergyParams P) {
     const int l[3] = {(tid >> 6) + 4 * h, (tid >> 3) & 7, tid & 7};
     const int ga = T[0] * kET + l[0], gb = T[1] * kET + l[1], gc = T[2] * kET + l[2];
     if (ga < v && gb < v && gc < v) {
+      // the 18 reads use only six distinct swizzled offsets: those of the six permutations of (la,lb,lc)
+      int swo[6];
+#pragma unroll
+      for (int pi = 0; pi < 6; ++pi) swo[pi] = sw_idx(l[PERM[pi][0]], l[PERM[pi][1]], l[PERM[pi][2]]);
       double w[6];
 #pragma unroll
       for (int pi = 0; pi < 6; ++pi) {
         const int s0 = PERM[pi][0], s1 = PERM[pi][1], s2 = PERM[pi][2];
         // element (e[s0], e[s1], e[s2]) of W = N_0[.s0.][.s1.][.s2.] + N_1[.s0.][.s2.][.s1.] + N_2[.s2.][.s1.][.s0.]
-        w[pi] = S[(0 * 6 + pi) * kETileElems + sw_idx(l[s0], l[s1], l[s2])] +
-                S[(1 * 6 + pi) * kETileElems + sw_idx(l[s0], l[s2], l[s1])] +
-                S[(2 * 6 + pi) * kETileElems + sw_idx(l[s2], l[s1], l[s0])];
+        w[pi] = S[(0 * 6 + pi) * kETileElems + swo[pi]] + S[(1 * 6 + pi) * kETileElems + swo[perm_index(s0, s2)]] +
+                S[(2 * 6 + pi) * kETileElems + swo[perm_index(s2, s1)]];
       }
       // Z_s = 4W_s + (two cyclic partners) - 2 (three transposed partners) = 3 W_s + S_same - 2 S_other, where
       // S_even = W[abc]+W[bca]+W[cab] (perms 0,1,2) and S_odd = W[cba]+W[acb]+W[bac] (perms 3,4,5)
@@ -171,9 +176,10 @@ t_energy_fused_kernel(const EnergyParams P) {
         const int s0 = PERM[pi][0], s1 = PERM[pi][1], s2 = PERM[pi][2];
         const double z = 3.0 * w[pi] + (pi < 3 ? s_even - 2.0 * s_odd : s_odd - 2.0 * s_even);
         // V for (a',b',c') = (e[s0], e[s1], e[s2]):  g_ij[a',b'] t1[c',k] + g_jk[b',c'] t1[a',i] + g_ik[a',c'] t1[b',j]
-        const double vv = Gs[((0 * 3 + s0) * 3 + s1) * 64 + l[s0] * 8 + l[s1]] * T1s[(2 * 3 + s2) * 8 + l[s2]] +
-                          Gs[((1 * 3 + s1) * 3 + s2) * 64 + l[s1] * 8 + l[s2]] * T1s[(0 * 3 + s0) * 8 + l[s0]] +
-                          Gs[((2 * 3 + s0) * 3 + s2) * 64 + l[s0] * 8 + l[s2]] * T1s[(1 * 3 + s1) * 8 + l[s1]];
+        const double vv =
+            Gs[((0 * 3 + s0) * 3 + s1) * kEGPatch + l[s0] * kEGPitch + l[s1]] * T1s[(2 * 3 + s2) * 8 + l[s2]] +
+            Gs[((1 * 3 + s1) * 3 + s2) * kEGPatch + l[s1] * kEGPitch + l[s2]] * T1s[(0 * 3 + s0) * 8 + l[s0]] +
+            Gs[((2 * 3 + s0) * 3 + s2) * kEGPatch + l[s0] * kEGPitch + l[s2]] * T1s[(1 * 3 + s1) * 8 + l[s1]];
         acc += (w[pi] + vv) * z;
       }
       const double d = eijk - Ev[l[0]] - Ev[8 + l[1]] - Ev[16 + l[2]];
