@@ -25,12 +25,12 @@
 namespace mpqc_t {
 
 constexpr int kET = 8;              // energy tile edge
-constexpr int kEThreads = 256;
+constexpr int kEThreads = 512;
 constexpr int kETileElems = kET * kET * kET;                 // 512 doubles
 constexpr int kEStageBytes = 18 * kETileElems * 8;           // 73,728 B of raw tiles
 constexpr int kEGPitch = 9;                                  // padded row pitch of the 8x8 g patches (bank conflicts)
 constexpr int kEGPatch = 8 * kEGPitch;                       // doubles per patch
-constexpr int kESmallDoubles = 27 * kEGPatch + 72 + 24 + 8;  // g patches, t1 slices, eps slices, reduction
+constexpr int kESmallDoubles = 27 * kEGPatch + 72 + 24 + 16;  // g patches, t1 slices, eps slices, reduction
 constexpr int kEnergySmemBytes = kEStageBytes + kESmallDoubles * 8;
 
 struct EnergyParams {
@@ -78,7 +78,7 @@ t_energy_fused_kernel(const EnergyParams P) {
   double* Gs = S + 18 * kETileElems;                            // [3][3][3][8][8]
   double* T1s = Gs + 27 * kEGPatch;                             // [3][3][8]
   double* Ev = T1s + 72;                                        // [3][8]
-  double* red = Ev + 24;                                        // [8]
+  double* red = Ev + 24;                                        // [16]
 
   constexpr int PERM[6][3] = MPQC_T_PERMS;
   const int b = blockIdx.y;
@@ -92,22 +92,23 @@ t_energy_fused_kernel(const EnergyParams P) {
 
   // ---- issue all 18 raw-tile copies: thread -> (row = tid>>2, 16-byte chunk = tid&3) of every tile ----
   {
-    const int row = tid >> 2, x = row >> 3, y = row & 7, z = (tid & 3) << 1;
+    const int cidx = tid & 255, half = tid >> 8;            // each half-block copies 9 of the 18 tiles
+    const int row = cidx >> 2, x = row >> 3, y = row & 7, z = (cidx & 3) << 1;
     const uint32_t s_base = smem_u32(S);
     const uint32_t dst_off = (uint32_t)sw_idx(x, y, z) * 8u;
 #pragma unroll
-    for (int pi = 0; pi < 6; ++pi) {
-      const int X = T[PERM[pi][0]], Y = T[PERM[pi][1]], Z = T[PERM[pi][2]];
-      // array 0 tile at (X,Y,Z); array 1 tile at (X,Z,Y); array 2 tile at (Z,Y,X)   [first][second][third]
-#pragma unroll
-      for (int g = 0; g < 3; ++g) {
+    for (int q = 0; q < 18; ++q) {
+      if ((q & 1) == half) {
+        const int g = q / 6, pi = q % 6;
+        const int X = T[PERM[pi][0]], Y = T[PERM[pi][1]], Z = T[PERM[pi][2]];
+        // array 0 tile at (X,Y,Z); array 1 tile at (X,Z,Y); array 2 tile at (Z,Y,X)   [first][second][third]
         const int t0 = g == 2 ? Z : X, t1 = g == 1 ? Z : Y, t2 = g == 0 ? Z : (g == 1 ? Y : X);
         const int g0 = t0 * kET + x, g1 = t1 * kET + y, g2 = t2 * kET + z;
         int nbytes = 0;
         if (g0 < v && g1 < v && g2 < v) nbytes = (g2 + 1 < v) ? 16 : 8;
         const double* src = nbase + g * nstride + ((int64_t)(g0 < v ? g0 : 0) * v + (g1 < v ? g1 : 0)) * ldw +
                             (g2 < v ? g2 : 0);
-        cp_async_16_zfill(s_base + (uint32_t)((g * 6 + pi) * kETileElems * 8) + dst_off, src, nbytes);
+        cp_async_16_zfill(s_base + (uint32_t)(q * kETileElems * 8) + dst_off, src, nbytes);
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -118,7 +119,7 @@ t_energy_fused_kernel(const EnergyParams P) {
   {
     const uint32_t g_base = smem_u32(Gs);
 #pragma unroll
-    for (int it = 0; it < 7; ++it) {
+    for (int it = 0; it < (27 * 64 + kEThreads - 1) / kEThreads; ++it) {
       const int e = it * kEThreads + tid;
       if (e < 27 * 64) {
         const int c = e & 7, r = (e >> 3) & 7, tcol = (e >> 6) % 3, trow = (e / 192) % 3, which = e / 576;
@@ -150,9 +151,8 @@ t_energy_fused_kernel(const EnergyParams P) {
 
   // ---- evaluate: thread owns (la,lb,lc) of the (TA,TB,TC) tile and all six permutations of it ----
   double sum = 0.0;
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int l[3] = {(tid >> 6) + 4 * h, (tid >> 3) & 7, tid & 7};
+  {
+    const int l[3] = {tid >> 6, (tid >> 3) & 7, tid & 7};
     const int ga = T[0] * kET + l[0], gb = T[1] * kET + l[1], gc = T[2] * kET + l[2];
     if (ga < v && gb < v && gc < v) {
       // the 18 reads use only six distinct swizzled offsets: those of the six permutations of (la,lb,lc)
