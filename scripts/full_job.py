@@ -22,7 +22,7 @@ del pd
 torch.cuda.empty_cache()
 prob = L.make_problem(o, v, host["eps_occ"], host["eps_vir"], host["t1"], host["t2"], host["g_abij"], host["g_aijk"], host["g_abci"])
 opt = L.Options()
-opt.ngpu, opt.unit_count, opt.use_nccl, opt.verbose = a.ngpu, -1, a.nccl, 1
+opt.ngpu, opt.unit_count, opt.use_nccl, opt.verbose = a.ngpu, -1, a.nccl, 2
 e, st = C.c_double(), L.Stats()
 t0 = time.perf_counter()
 L.check(lib.mpqc_t_energy(C.byref(prob), C.byref(opt), C.byref(e), C.byref(st)), "mpqc_t_energy")
