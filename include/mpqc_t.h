@@ -63,6 +63,25 @@ typedef struct mpqc_t_problem {
   const double* g_abci;   /* [v][v][v][o] */
 } mpqc_t_problem;
 
+/* Density-fitted form of the same inputs: instead of the three four-index integral
+ * classes the caller hands the three-centre factors the reference's CCSD already holds when is_df() is true,
+ *   Xab[K][a][b] = (K|G|a b)[inv_sqr]   CCSD::get_Xab()  ccsd.h:480-483
+ *   Xij[K][i][j] = (K|G|i j)[inv_sqr]   CCSD::get_Xij()  ccsd.h:485-488
+ *   Xai[K][a][i] = (K|G|a i)[inv_sqr]   CCSD::get_Xai()  ccsd.h:490-493
+ * and the library forms  <ij|ab> = sum_K Xai[K,a,i] Xai[K,b,j],  <ij|ka> = sum_K Xij[K,i,k] Xai[K,a,j],
+ * <ia|bc> = sum_K Xai[K,b,i] Xab[K,a,c]  directly in their occupied-major device layouts (what the [df] getters
+ * of ccsd_t.h:2210-2244 evaluate on the host).  The v^3 o tensor never exists on the host or crosses PCIe. */
+typedef struct mpqc_t_df_problem {
+  int64_t o, v, naux;
+  const double* eps_occ;  /* [o] */
+  const double* eps_vir;  /* [v] */
+  const double* t1;       /* [v][o] */
+  const double* t2;       /* [v][v][o][o] */
+  const double* x_ab;     /* [naux][v][v] */
+  const double* x_ij;     /* [naux][o][o] */
+  const double* x_ai;     /* [naux][v][o] */
+} mpqc_t_df_problem;
+
 typedef struct mpqc_t_options {
   int32_t ngpu;               /* number of devices this process drives (>=1); 0 -> 1 */
   const int32_t* device_ids;  /* [ngpu] CUDA ordinals, NULL -> 0..ngpu-1 */
@@ -101,10 +120,15 @@ typedef struct mpqc_t_handle mpqc_t_handle; /* opaque: one device's resident, re
  * unit_count<0).  Caller owns every buffer for the duration of the call; nothing is retained. */
 int mpqc_t_energy(const mpqc_t_problem* p, const mpqc_t_options* opt, double* e_t, mpqc_t_stats* stats);
 
+/* same contract, density-fitted inputs */
+int mpqc_t_energy_df(const mpqc_t_df_problem* p, const mpqc_t_options* opt, double* e_t, mpqc_t_stats* stats);
+
 /* ---- split-phase API (lets uploads be timed separately; used by bench.py and the tests) ------ */
 int mpqc_t_create(mpqc_t_handle** h, int64_t o, int64_t v, int32_t device);
 /* host (on_device=0) or device (on_device=1) buffers -> occupied-major operand layouts in HBM */
 int mpqc_t_upload(mpqc_t_handle* h, const mpqc_t_problem* p, int32_t on_device, mpqc_t_stats* stats);
+/* density-fitted inputs -> the same device layouts (integrals assembled on the device with cuBLAS DGEMMs) */
+int mpqc_t_upload_df(mpqc_t_handle* h, const mpqc_t_df_problem* p, int32_t on_device, mpqc_t_stats* stats);
 /* process units first, first+stride, ... (count of them; <0 = to the end).  partial_e = weighted sum
  * over those units (summed in unit order, so any sharding gives bit-identical per-unit terms);
  * unit_e (optional, may be NULL) receives the weighted per-unit energies [count].  batch 0 = auto. */

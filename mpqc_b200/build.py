@@ -29,6 +29,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    # no link-time library dependencies: NCCL and cuBLAS (density-fitted upload only) are bound with dlopen
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

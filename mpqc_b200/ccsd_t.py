@@ -98,6 +98,11 @@ class DenseCCSD:
     orbital_energies: object
     n_frozen: int = 0
     e_ccsd: float = 0.0
+    # optional density-fitting factors (CCSD::get_Xab / get_Xij / get_Xai, ccsd.h:480-493); when present and
+    # is_df() the (T) driver hands THEM to the library and the v^3 o tensor is assembled on the device
+    x_ab: object = None
+    x_ij: object = None
+    x_ai: object = None
     _engine: TRange1Engine = field(default=None, repr=False)
 
     def __post_init__(self):
@@ -132,6 +137,18 @@ class DenseCCSD:
     def ccsd_energy(self):
         return self.e_ccsd
 
+    def is_df(self):                                   # ccsd.h:93-99: method == "df"
+        return self.x_ab is not None and self.x_ij is not None and self.x_ai is not None
+
+    def get_Xab(self):
+        return self.x_ab
+
+    def get_Xij(self):
+        return self.x_ij
+
+    def get_Xai(self):
+        return self.x_ai
+
     @classmethod
     def from_problem(cls, p: dict, n_frozen: int = 0, e_ccsd: float = 0.0, frozen_eps=None):
         """Wrap a ``synthetic.make_problem`` dict (optionally prepending frozen-core energies)."""
@@ -150,7 +167,8 @@ class DenseCCSD:
             else:
                 import torch
                 eps = torch.cat([p["eps_occ"], p["eps_vir"]])
-        return cls(p["t1"], p["t2"], p["g_abij"], p["g_aijk"], p["g_abci"], eps, n_frozen, e_ccsd)
+        return cls(p["t1"], p["t2"], p["g_abij"], p["g_aijk"], p["g_abci"], eps, n_frozen, e_ccsd,
+                   p.get("x_ab"), p.get("x_ij"), p.get("x_ai"))
 
 
 class Energy:
@@ -204,6 +222,9 @@ class CCSD_T:
         self.device_ids_ = kv.get("device_ids")
         self.batch_ = int(kv.get("batch", 0))
         self.use_nccl_ = bool(kv.get("use_nccl", False))
+        # "df_direct": with a density-fitted CCSD (method df) assemble the integrals on the device from the
+        # three-centre factors instead of receiving the dense <ia|bc> tensor
+        self.df_direct_ = bool(kv.get("df_direct", False))
         self.rank_ = int(kv.get("rank", 0))
         self.world_size_ = int(kv.get("world_size", 1))
         if self.ngpu_ < 1:
@@ -264,8 +285,16 @@ class CCSD_T:
             eps_vir = np.ascontiguousarray(eps_vir, dtype=np.float64)
         else:
             eps_occ, eps_vir = eps_occ.contiguous(), eps_vir.contiguous()
-        prob = L.make_problem(o, v, eps_occ, eps_vir, cc.t1(), cc.t2(), cc.get_abij(), cc.get_aijk(),
-                              cc.get_abci())
+        use_df = self.df_direct_ and hasattr(cc, "is_df") and cc.is_df()
+        if self.df_direct_ and not use_df:
+            raise InputError("df_direct requested but the CCSD provider has no density-fitting factors", "df_direct")
+        if use_df:
+            naux = cc.get_Xab().shape[0]
+            prob = L.make_df_problem(o, v, naux, eps_occ, eps_vir, cc.t1(), cc.t2(), cc.get_Xab(), cc.get_Xij(),
+                                     cc.get_Xai())
+        else:
+            prob = L.make_problem(o, v, eps_occ, eps_vir, cc.t1(), cc.t2(), cc.get_abij(), cc.get_aijk(),
+                                  cc.get_abci())
         opt = L.Options()
         opt.ngpu = self.ngpu_
         if self.device_ids_ is not None:
@@ -281,8 +310,11 @@ class CCSD_T:
         st = L.Stats()
         e = C.c_double(0.0)
         lib = L.load()
-        status = lib.mpqc_t_energy(C.byref(prob), C.byref(opt), C.byref(e), C.byref(st))
-        _raise_for(status, "mpqc_t_energy")
+        if use_df:
+            status = lib.mpqc_t_energy_df(C.byref(prob), C.byref(opt), C.byref(e), C.byref(st))
+        else:
+            status = lib.mpqc_t_energy(C.byref(prob), C.byref(opt), C.byref(e), C.byref(st))
+        _raise_for(status, "mpqc_t_energy_df" if use_df else "mpqc_t_energy")
         self.triples_energy_ = e.value
         self.stats_ = st.as_dict()
         print(f"(T) Energy: {self.triples_energy_} Time: {time.perf_counter() - t0} S ", file=self._out)

@@ -15,7 +15,10 @@
 #include <thread>
 #include <vector>
 
+#include <cublas_v2.h>
 #include <dlfcn.h>
+
+#include <functional>
 
 #include "common.cuh"
 #include "microbench.cuh"
@@ -109,6 +112,38 @@ const NcclApi& nccl_api() {
   });
   return api;
 }
+// ---- cuBLAS, bound at run time for the same reasons (plain library DGEMMs of the density-fitted upload only) ----
+struct BlasApi {
+  cublasStatus_t (*Create)(cublasHandle_t*) = nullptr;
+  cublasStatus_t (*Destroy)(cublasHandle_t) = nullptr;
+  cublasStatus_t (*SetStream)(cublasHandle_t, cudaStream_t) = nullptr;
+  cublasStatus_t (*DgemmStridedBatched)(cublasHandle_t, cublasOperation_t, cublasOperation_t, int, int, int,
+                                        const double*, const double*, int, long long, const double*, int, long long,
+                                        const double*, double*, int, long long, int) = nullptr;
+  bool ok = false;
+};
+
+const BlasApi& blas_api() {
+  static BlasApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* names[] = {"libcublas.so.12", "libcublas.so"};
+    void* hnd = nullptr;
+    for (const char* n : names) {
+      hnd = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (hnd) break;
+    }
+    if (!hnd) return;
+    api.Create = reinterpret_cast<decltype(api.Create)>(dlsym(hnd, "cublasCreate_v2"));
+    api.Destroy = reinterpret_cast<decltype(api.Destroy)>(dlsym(hnd, "cublasDestroy_v2"));
+    api.SetStream = reinterpret_cast<decltype(api.SetStream)>(dlsym(hnd, "cublasSetStream_v2"));
+    api.DgemmStridedBatched =
+        reinterpret_cast<decltype(api.DgemmStridedBatched)>(dlsym(hnd, "cublasDgemmStridedBatched"));
+    api.ok = api.Create && api.Destroy && api.SetStream && api.DgemmStridedBatched;
+  });
+  return api;
+}
+
 constexpr int kNcclFloat64 = 8;   // ncclDouble
 constexpr int kNcclSum = 0;
 
@@ -137,6 +172,7 @@ struct mpqc_t_handle {
   int64_t units_cap = 0;
   int* triples_dev = nullptr;
   double* unit_e_dev = nullptr;
+  cublasHandle_t blas = nullptr;   // only for the density-fitted upload (plain library DGEMMs)
 };
 
 namespace {
@@ -311,6 +347,21 @@ int launch_energy(mpqc_t_handle* h, int nbatch, const int* triples_dev, double* 
   return MPQC_T_OK;
 }
 
+// CUDA events released on every exit path
+struct EventList {
+  std::vector<cudaEvent_t> ev;
+  int add(cudaEvent_t* out) {
+    cudaEvent_t e;
+    MPQC_T_CUDA(cudaEventCreate(&e));
+    ev.push_back(e);
+    *out = e;
+    return MPQC_T_OK;
+  }
+  ~EventList() {
+    for (auto e : ev) cudaEventDestroy(e);
+  }
+};
+
 // copy host->device (or alias a device pointer) for the small/medium inputs
 struct Staged {
   const double* ptr = nullptr;
@@ -425,6 +476,104 @@ int upload_impl(mpqc_t_handle* h, const mpqc_t_problem* p, bool on_device, mpqc_
   return MPQC_T_OK;
 }
 
+#define MPQC_T_BLAS(expr)                                                                   \
+  do {                                                                                      \
+    cublasStatus_t _bs = (expr);                                                            \
+    if (_bs != CUBLAS_STATUS_SUCCESS) {                                                     \
+      char _buf[256];                                                                       \
+      snprintf(_buf, sizeof(_buf), "%s -> cuBLAS status %d", #expr, (int)_bs);              \
+      return fail(_bs == CUBLAS_STATUS_ALLOC_FAILED ? MPQC_T_ERR_OOM : MPQC_T_ERR_CUDA, _buf, __FILE__, __LINE__); \
+    }                                                                                       \
+  } while (0)
+
+// Density-fitted upload: the three integral classes are assembled on the device, straight into the operand layouts,
+// from the three-centre factors (what the reference's [df] formulas evaluate through TiledArray on the host,
+// ccsd_t.h:2210-2244 with is_df()).  These are plain strided-batched library DGEMMs (cuBLAS), one-time, ~2 naux v^3 o
+// FLOPs for each of A and AT; the triples loop itself is unchanged.
+int upload_df_impl(mpqc_t_handle* h, const mpqc_t_df_problem* p, bool on_device, mpqc_t_stats* stats) {
+  const int64_t o = h->o, v = h->v, Kp = h->Kp, naux = p->naux;
+  cudaStream_t st = h->stream;
+  int64_t launches = 0, h2d = 0;
+  const double t0 = now_s();
+  double t_copy = 0.0;
+  const BlasApi& bl = blas_api();
+  MPQC_T_CHECK(bl.ok, MPQC_T_ERR_CUDA, "density-fitted upload needs libcublas.so.12, which could not be loaded");
+  if (!h->blas) {
+    MPQC_T_BLAS(bl.Create(&h->blas));
+    MPQC_T_BLAS(bl.SetStream(h->blas, st));   // pointer mode defaults to host
+  }
+  MPQC_T_CUDA(cudaMemsetAsync(h->A, 0, (size_t)o * v * v * Kp * sizeof(double), st));
+  MPQC_T_CUDA(cudaMemsetAsync(h->B, 0, (size_t)o * o * v * Kp * sizeof(double), st));
+  if (h->flat) MPQC_T_CUDA(cudaMemsetAsync(h->AT, 0, (size_t)o * v * v * Kp * sizeof(double), st));
+
+  const double tc = now_s();
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  MPQC_T_CUDA(cudaMemcpyAsync(h->eps_occ, p->eps_occ, o * sizeof(double), kind, st));
+  MPQC_T_CUDA(cudaMemcpyAsync(h->eps_vir, p->eps_vir, v * sizeof(double), kind, st));
+  if (!on_device) h2d += (o + v) * 8;
+  Staged t1, t2, xab, xij, xai;
+  MPQC_T_TRY(stage_in(t1, p->t1, (size_t)v * o, on_device, st, &h2d));
+  MPQC_T_TRY(stage_in(t2, p->t2, (size_t)v * v * o * o, on_device, st, &h2d));
+  MPQC_T_TRY(stage_in(xab, p->x_ab, (size_t)naux * v * v, on_device, st, &h2d));
+  MPQC_T_TRY(stage_in(xij, p->x_ij, (size_t)naux * o * o, on_device, st, &h2d));
+  MPQC_T_TRY(stage_in(xai, p->x_ai, (size_t)naux * v * o, on_device, st, &h2d));
+  if (!on_device) {
+    MPQC_T_CUDA(cudaStreamSynchronize(st));
+    t_copy += now_s() - tc;
+  }
+  // XaiT[x][K][a] = Xai[K][a][x]  (unit stride on the virtual index for the GEMMs below)
+  double* xait = nullptr;
+  MPQC_T_CUDA(cudaMalloc(&xait, (size_t)o * naux * v * sizeof(double)));
+  Staged xait_owner;
+  xait_owner.owned = xait;
+  // in[kap = K][mid = a][j = x] -> out[x * naux*v + K * v + a]: generic transpose wants kap last, so treat
+  // (K,a) flattened as kap: in[(K a)][1][x] -> out[x][(K a)]
+  MPQC_T_TRY(launch_transpose(st, xai.ptr, xait, naux * v, 1, o, 1, naux * v, 0, 0, &launches));
+
+  // amplitude parts (same as the dense upload)
+  MPQC_T_TRY(launch_transpose(st, t1.ptr, h->T1T, v, 1, o, 1, v, 0, 0, &launches));
+  MPQC_T_TRY(launch_transpose(st, t2.ptr, h->B, v, v, o * o, 1, v * Kp, 0, Kp, &launches));
+  MPQC_T_TRY(launch_copy_hole(st, t2.ptr, h->A, v * v, o, o, v, v * Kp, Kp, v * v * Kp, v, -1.0, &launches));
+  if (h->flat)
+    MPQC_T_TRY(launch_copy_hole(st, t2.ptr, h->AT, v * v, o, o, v, Kp, v * Kp, v * v * Kp, v, -1.0, &launches));
+
+  const double one = 1.0, zero = 0.0;
+  const int iv = (int)v, io = (int)o, ik = (int)naux;
+  // All GEMMs below are column-major C_cm(m x n) = op(A_cm) op(B_cm); row-major targets are written as their transposes.
+  for (int64_t x = 0; x < o; ++x) {
+    const double* xt = xait + x * naux * v;                       // (a, K) column-major, ld = v
+    // A[x][p][q][kap] = sum_K Xai[K,p,x] Xab[K,q,kap]:  for each q: C_cm(kap, p), ldc = v*Kp
+    MPQC_T_BLAS(bl.DgemmStridedBatched(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, iv, iv, ik, &one, xab.ptr, iv * iv, v,
+                                          xt, iv, 0, &zero, h->A + x * v * v * Kp, (int)(v * Kp), Kp, iv));
+    ++launches;
+    if (h->flat) {
+      // AT[x][p][q][kap] = sum_K Xai[K,q,x] Xab[K,p,kap]:  for each p: C_cm(kap, q), ldc = Kp
+      MPQC_T_BLAS(bl.DgemmStridedBatched(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, iv, iv, ik, &one, xab.ptr, iv * iv, v,
+                                            xt, iv, 0, &zero, h->AT + x * v * v * Kp, (int)Kp, v * Kp, iv));
+      ++launches;
+    }
+    // GV[x][j][a][b] = sum_K Xai[K,a,x] Xai[K,b,j]:  for each j: C_cm(b, a) = XaiT[j](b,K) XaiT[x](a,K)^T
+    MPQC_T_BLAS(bl.DgemmStridedBatched(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, iv, iv, ik, &one, xait, iv, naux * v, xt,
+                                          iv, 0, &zero, h->GV + x * o * v * v, iv, v * v, io));
+    ++launches;
+    // B[y][x][r][v + l] = g_aijk[r,y,x,l] = sum_K Xij[K,y,l] Xai[K,r,x]:  for each y: C_cm(l, r), ldc = Kp
+    MPQC_T_BLAS(bl.DgemmStridedBatched(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, io, iv, ik, &one, xij.ptr, io * io, o, xt,
+                                          iv, 0, &zero, h->B + x * v * Kp + v, (int)Kp, o * v * Kp, io));
+    ++launches;
+  }
+  MPQC_T_CUDA(cudaStreamSynchronize(st));
+  MPQC_T_CUDA(cudaGetLastError());
+  h->uploaded = true;
+  if (stats) {
+    double tot = now_s() - t0;
+    stats->seconds_upload += t_copy;
+    stats->seconds_relayout += tot - t_copy;
+    stats->kernel_launches += launches;
+    stats->bytes_h2d += h2d;
+  }
+  return MPQC_T_OK;
+}
+
 // Run an explicit list of units (indices into the global enumeration).  unit_e_host[n] receives the
 // weighted per-unit energies.  Synchronises the stream before returning.
 int run_units(mpqc_t_handle* h, const std::vector<int>& all_triples, const int64_t* units, int64_t n, int batch,
@@ -434,6 +583,10 @@ int run_units(mpqc_t_handle* h, const std::vector<int>& all_triples, const int64
   if (batch <= 0) batch = auto_batch(h);
   batch = (int)std::min<int64_t>(batch, n);
   batch = std::min(batch, 65535);
+  {  // tile indices are 32-bit
+    const int64_t tiles_per_triple = 3LL * h->nmt * h->nnt;
+    batch = (int)std::max<int64_t>(1, std::min<int64_t>(batch, ((1LL << 31) - 1) / tiles_per_triple));
+  }
   MPQC_T_TRY(ensure_work(h, batch));
   MPQC_T_TRY(ensure_units(h, n));
   std::vector<int> tri((size_t)n * 3);
@@ -443,13 +596,14 @@ int run_units(mpqc_t_handle* h, const std::vector<int>& all_triples, const int64
 
   const int64_t nbatches = (n + batch - 1) / batch;
   profile = profile && nbatches <= 8192;
+  EventList events;
   std::vector<cudaEvent_t> ev;
   cudaEvent_t e_begin, e_end;
-  MPQC_T_CUDA(cudaEventCreate(&e_begin));
-  MPQC_T_CUDA(cudaEventCreate(&e_end));
+  MPQC_T_TRY(events.add(&e_begin));
+  MPQC_T_TRY(events.add(&e_end));
   if (profile) {
     ev.resize((size_t)nbatches * 3);
-    for (auto& e : ev) MPQC_T_CUDA(cudaEventCreate(&e));
+    for (auto& e : ev) MPQC_T_TRY(events.add(&e));
   }
   MPQC_T_CUDA(cudaEventRecord(e_begin, h->stream));
   int64_t launches = 0;
@@ -491,9 +645,6 @@ int run_units(mpqc_t_handle* h, const std::vector<int>& all_triples, const int64
     stats->bytes_d2h += n * 8;
     stats->bytes_h2d += n * 12;
   }
-  for (auto& e : ev) cudaEventDestroy(e);
-  cudaEventDestroy(e_begin);
-  cudaEventDestroy(e_end);
   return MPQC_T_OK;
 }
 
@@ -656,6 +807,7 @@ int mpqc_t_destroy(mpqc_t_handle* h) {
   cudaFree(h->tile_sets);
   cudaFree(h->triples_dev);
   cudaFree(h->unit_e_dev);
+  if (h->blas && blas_api().ok) blas_api().Destroy(h->blas);
   if (h->stream) cudaStreamDestroy(h->stream);
   cudaGetLastError();
   delete h;
@@ -726,9 +878,18 @@ int mpqc_t_debug_w(mpqc_t_handle* h, int32_t i, int32_t j, int32_t k, double* w_
   return MPQC_T_OK;
 }
 
-int mpqc_t_energy(const mpqc_t_problem* p, const mpqc_t_options* opt_in, double* e_t, mpqc_t_stats* stats_out) {
-  MPQC_T_CHECK(e_t != nullptr, MPQC_T_ERR_BAD_ARG, "e_t is NULL");
-  MPQC_T_TRY(validate_problem(p));
+}  // extern "C"
+
+namespace {
+
+typedef std::function<int(mpqc_t_handle*, mpqc_t_stats*)> UploadFn;
+
+// Shared driver of the one-shot entry points: shard the units over this process' GPUs (static share + work-stealing
+// tail), run them, sum the partial energies (host, or one ncclAllReduce).  `upload` puts the inputs on one handle.
+int energy_impl(const int64_t prob_o, const int64_t prob_v, const UploadFn& upload, const mpqc_t_options* opt_in,
+                double* e_t, mpqc_t_stats* stats_out) {
+  struct { int64_t o, v; } pp = {prob_o, prob_v};
+  const auto* p = &pp;
   mpqc_t_options opt;
   memset(&opt, 0, sizeof(opt));
   if (opt_in) opt = *opt_in;
@@ -816,7 +977,7 @@ int mpqc_t_energy(const mpqc_t_problem* p, const mpqc_t_options* opt_in, double*
     const double tw0 = now_s();
     int rc = mpqc_t_create(&h, p->o, p->v, devs[g]);
     const double tw1 = now_s();
-    if (rc == MPQC_T_OK) rc = mpqc_t_upload(h, p, opt.inputs_on_device, &gs);
+    if (rc == MPQC_T_OK) rc = upload(h, &gs);
     const double tw2 = now_s();
     if (workers_uploaded.fetch_add(1) + 1 == ngpu) nccl_start();
     if (rc == MPQC_T_OK) {
@@ -937,6 +1098,44 @@ int mpqc_t_energy(const mpqc_t_problem* p, const mpqc_t_options* opt_in, double*
   }
   if (stats_out) *stats_out = stats;
   return MPQC_T_OK;
+}
+
+int validate_df_problem(const mpqc_t_df_problem* p) {
+  MPQC_T_CHECK(p != nullptr, MPQC_T_ERR_BAD_ARG, "problem is NULL");
+  MPQC_T_CHECK(p->o >= 1 && p->v >= 1 && p->naux >= 1, MPQC_T_ERR_BAD_ARG, "o, v and naux must be >= 1");
+  MPQC_T_CHECK(p->o <= 4096 && p->v <= 2040 && p->naux <= (1 << 20), MPQC_T_ERR_BAD_ARG,
+               "o <= 4096, v <= 2040, naux <= 2^20 supported");
+  MPQC_T_CHECK(p->eps_occ && p->eps_vir && p->t1 && p->t2 && p->x_ab && p->x_ij && p->x_ai, MPQC_T_ERR_BAD_ARG,
+               "a tensor pointer is NULL");
+  return MPQC_T_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mpqc_t_energy(const mpqc_t_problem* p, const mpqc_t_options* opt, double* e_t, mpqc_t_stats* stats) {
+  MPQC_T_CHECK(e_t != nullptr, MPQC_T_ERR_BAD_ARG, "e_t is NULL");
+  MPQC_T_TRY(validate_problem(p));
+  const int on_dev = opt ? opt->inputs_on_device : 0;
+  return energy_impl(p->o, p->v, [&](mpqc_t_handle* h, mpqc_t_stats* st) { return mpqc_t_upload(h, p, on_dev, st); },
+                     opt, e_t, stats);
+}
+
+int mpqc_t_energy_df(const mpqc_t_df_problem* p, const mpqc_t_options* opt, double* e_t, mpqc_t_stats* stats) {
+  MPQC_T_CHECK(e_t != nullptr, MPQC_T_ERR_BAD_ARG, "e_t is NULL");
+  MPQC_T_TRY(validate_df_problem(p));
+  const int on_dev = opt ? opt->inputs_on_device : 0;
+  return energy_impl(p->o, p->v, [&](mpqc_t_handle* h, mpqc_t_stats* st) { return mpqc_t_upload_df(h, p, on_dev, st); },
+                     opt, e_t, stats);
+}
+
+int mpqc_t_upload_df(mpqc_t_handle* h, const mpqc_t_df_problem* p, int32_t on_device, mpqc_t_stats* stats) {
+  MPQC_T_CHECK(h != nullptr, MPQC_T_ERR_BAD_ARG, "handle is NULL");
+  MPQC_T_TRY(validate_df_problem(p));
+  MPQC_T_CHECK(p->o == h->o && p->v == h->v, MPQC_T_ERR_BAD_ARG, "problem dimensions differ from the handle's");
+  MPQC_T_CUDA(cudaSetDevice(h->device));
+  return upload_df_impl(h, p, on_device != 0, stats);
 }
 
 int mpqc_t_microbench(int32_t device, int32_t which, double* tflops) {

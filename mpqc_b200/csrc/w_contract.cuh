@@ -80,10 +80,12 @@ __device__ __forceinline__ void decode_tile(const GemmParams& P, int tile, int& 
     nt = P.nnt - 1;
     t = tile - P.main_tiles;
   }
-  mt = t % P.nmt;
-  t /= P.nmt;
+  // group fastest, then row tile: the CTAs of one wave that share a row tile read the same operand panels
+  // (A_i: g = 0,1 term 0;  AT_j: g = 0,2 term 1;  A_k / AT_k: g = 2 / g = 1) while they are still in L2
   g = t % 3;
-  b = t / 3;
+  t /= 3;
+  mt = t % P.nmt;
+  b = t / P.nmt;
 }
 
 // compile-time chunking of the NFRAG column fragments into register chunks of nearly equal size

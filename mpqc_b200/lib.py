@@ -24,6 +24,12 @@ class Problem(C.Structure):
                 ("g_abij", C.c_void_p), ("g_aijk", C.c_void_p), ("g_abci", C.c_void_p)]
 
 
+class DfProblem(C.Structure):
+    _fields_ = [("o", C.c_int64), ("v", C.c_int64), ("naux", C.c_int64),
+                ("eps_occ", C.c_void_p), ("eps_vir", C.c_void_p), ("t1", C.c_void_p), ("t2", C.c_void_p),
+                ("x_ab", C.c_void_p), ("x_ij", C.c_void_p), ("x_ai", C.c_void_p)]
+
+
 class Options(C.Structure):
     _fields_ = [("ngpu", C.c_int32), ("device_ids", C.POINTER(C.c_int32)), ("verbose", C.c_int32),
                 ("inputs_on_device", C.c_int32), ("unit_first", C.c_int64), ("unit_stride", C.c_int64),
@@ -50,7 +56,7 @@ class MpqcTError(RuntimeError):
 
 #: every symbol include/mpqc_t.h declares (tests check the .so exports all of them)
 SYMBOLS = [
-    "mpqc_t_energy", "mpqc_t_create", "mpqc_t_upload", "mpqc_t_run", "mpqc_t_debug_w", "mpqc_t_stream",
+    "mpqc_t_energy", "mpqc_t_energy_df", "mpqc_t_create", "mpqc_t_upload", "mpqc_t_upload_df", "mpqc_t_run", "mpqc_t_debug_w", "mpqc_t_stream",
     "mpqc_t_destroy", "mpqc_t_triple_count", "mpqc_t_triple_of_unit", "mpqc_t_flops", "mpqc_t_unit_flops",
     "mpqc_t_device_count", "mpqc_t_version", "mpqc_t_strerror", "mpqc_t_last_error", "mpqc_t_microbench",
 ]
@@ -71,6 +77,10 @@ def load() -> C.CDLL:
     vp = C.c_void_p
     lib.mpqc_t_energy.argtypes = [C.POINTER(Problem), C.POINTER(Options), c_double_p, C.POINTER(Stats)]
     lib.mpqc_t_energy.restype = C.c_int
+    lib.mpqc_t_energy_df.argtypes = [C.POINTER(DfProblem), C.POINTER(Options), c_double_p, C.POINTER(Stats)]
+    lib.mpqc_t_energy_df.restype = C.c_int
+    lib.mpqc_t_upload_df.argtypes = [vp, C.POINTER(DfProblem), C.c_int32, C.POINTER(Stats)]
+    lib.mpqc_t_upload_df.restype = C.c_int
     lib.mpqc_t_create.argtypes = [C.POINTER(vp), C.c_int64, C.c_int64, C.c_int32]
     lib.mpqc_t_create.restype = C.c_int
     lib.mpqc_t_upload.argtypes = [vp, C.POINTER(Problem), C.c_int32, C.POINTER(Stats)]
@@ -133,5 +143,18 @@ def make_problem(o, v, eps_occ, eps_vir, t1, t2, g_abij, g_aijk, g_abci):
         if tuple(arrs[k].shape) != shp:
             raise ValueError(f"{k} has shape {tuple(arrs[k].shape)}, expected {shp}")
     p = Problem(o=o, v=v, **{k: _ptr(a) for k, a in arrs.items()})
+    p._keepalive = arrs
+    return p
+
+
+def make_df_problem(o, v, naux, eps_occ, eps_vir, t1, t2, x_ab, x_ij, x_ai):
+    """Density-fitted inputs: x_ab[naux,v,v] (symmetric in a,b), x_ij[naux,o,o], x_ai[naux,v,o]."""
+    shapes = dict(eps_occ=(o,), eps_vir=(v,), t1=(v, o), t2=(v, v, o, o), x_ab=(naux, v, v), x_ij=(naux, o, o),
+                  x_ai=(naux, v, o))
+    arrs = dict(eps_occ=eps_occ, eps_vir=eps_vir, t1=t1, t2=t2, x_ab=x_ab, x_ij=x_ij, x_ai=x_ai)
+    for k, shp in shapes.items():
+        if tuple(arrs[k].shape) != shp:
+            raise ValueError(f"{k} has shape {tuple(arrs[k].shape)}, expected {shp}")
+    p = DfProblem(o=o, v=v, naux=naux, **{k: _ptr(a) for k, a in arrs.items()})
     p._keepalive = arrs
     return p

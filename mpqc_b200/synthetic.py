@@ -56,7 +56,10 @@ def make_problem(o: int, v: int, seed: int = SEED, scale: float | None = None, n
     return dict(o=o, v=v, eps_occ=eps_occ, eps_vir=eps_vir,
                 t1=np.ascontiguousarray(t1), t2=np.ascontiguousarray(t2),
                 g_abij=np.ascontiguousarray(g_abij), g_aijk=np.ascontiguousarray(g_aijk),
-                g_abci=np.ascontiguousarray(g_abci))
+                g_abci=np.ascontiguousarray(g_abci),
+                # the three-centre factors in the reference's layouts (CCSD::get_Xab/Xij/Xai, ccsd.h:480-493)
+                naux=naux, x_ab=np.ascontiguousarray(l_vv), x_ij=np.ascontiguousarray(l_oo),
+                x_ai=np.ascontiguousarray(l_ov.transpose(0, 2, 1)))
 
 
 def make_problem_torch(o: int, v: int, device, seed: int = SEED, scale: float | None = None,
@@ -103,4 +106,5 @@ def make_problem_torch(o: int, v: int, device, seed: int = SEED, scale: float | 
     t2 = (g_abij / d2).contiguous()
     t1 = torch.randn(v, o, generator=g, device=device, dtype=f64) * 0.02
     return dict(o=o, v=v, eps_occ=eps_occ, eps_vir=eps_vir, t1=t1, t2=t2,
-                g_abij=g_abij, g_aijk=g_aijk, g_abci=g_abci)
+                g_abij=g_abij, g_aijk=g_aijk, g_abci=g_abci, naux=naux, x_ab=l_vv.contiguous(),
+                x_ij=l_oo.contiguous(), x_ai=l_ov.transpose(1, 2).contiguous())

@@ -212,6 +212,44 @@ def test_in_process_multi_gpu_matches_single(lib, use_nccl):
     assert abs(e1 - oc.ijk_driven(*_args(p))) < TOL
 
 
+@pytest.mark.parametrize("o,v", [(3, 9), (5, 26), (6, 41)])
+def test_density_fitted_inputs_match_dense_inputs(lib, o, v):
+    # integrals assembled on the device from the three-centre factors (cuBLAS DGEMMs straight into
+    # the operand layouts) must give the same E(T) as the dense tensors the reference's getters produce
+    p = make_problem(o, v, seed=50 + v)
+    e_dense, _ = _energy_oneshot(lib, p)
+    dfp = L.make_df_problem(o, v, p["naux"], p["eps_occ"], p["eps_vir"], p["t1"], p["t2"], p["x_ab"], p["x_ij"], p["x_ai"])
+    opt = L.Options()
+    opt.ngpu, opt.unit_count = 1, -1
+    e, st = C.c_double(), L.Stats()
+    L.check(lib.mpqc_t_energy_df(C.byref(dfp), C.byref(opt), C.byref(e), C.byref(st)), "mpqc_t_energy_df")
+    assert abs(e.value - e_dense) < 1e-12
+    assert abs(e.value - oc.ijk_driven(*_args(p))) < TOL
+    assert st.bytes_h2d < 8 * (p["t2"].size + p["x_ab"].size + p["x_ij"].size + p["x_ai"].size + p["t1"].size + o + v) + 64 * st.units
+    # and through the plugin interface (df_direct keyword), both flat and patch row modes
+    wfn = CCSD_T({"type": "CCSD(T)", "method": "df", "df_direct": True}, ccsd=DenseCCSD.from_problem(p), out=io.StringIO())
+    assert abs(wfn.compute_ccsd_t() - e_dense) < 1e-12
+
+
+def test_density_fitted_device_inputs_patch_mode(lib):
+    os.environ["MPQC_T_FLAT"] = "0"
+    try:
+        p = make_problem_torch(7, 52, "cuda", seed=77)
+        h = Handle(lib, p, on_device=True)
+        e_dense, ue_dense, _ = h.run()
+        h.close()
+        hh = C.c_void_p()
+        L.check(lib.mpqc_t_create(C.byref(hh), 7, 52, 0), "create")
+        dfp = L.make_df_problem(7, 52, p["naux"], p["eps_occ"], p["eps_vir"], p["t1"], p["t2"], p["x_ab"], p["x_ij"], p["x_ai"])
+        L.check(lib.mpqc_t_upload_df(hh, C.byref(dfp), 1, None), "upload_df")
+        e, st = C.c_double(), L.Stats()
+        L.check(lib.mpqc_t_run(hh, 0, 1, -1, 0, C.byref(e), None, C.byref(st)), "run")
+        lib.mpqc_t_destroy(hh)
+        assert abs(e.value - e_dense) < 1e-12
+    finally:
+        del os.environ["MPQC_T_FLAT"]
+
+
 def test_h2o_reference_golden_value(lib):
     # the reference's own stored (T) for H2O/6-31G (tests/validation/reference/outputs/h2o-ccsd_t-631g-pvdz.out:395)
     # from the committed tensor fixture, through the plugin interface with its frozen core (o=4, v=8)

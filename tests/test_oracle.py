@@ -153,3 +153,14 @@ def test_h2o_fixture_is_reproducible():
     assert abs(e_t["straight"] - REF_T) < 1e-11
     # amplitudes are defined up to orbital phases, which E(T) is invariant to: compare invariants
     assert abs(np.linalg.norm(cc["t2"]) - np.linalg.norm(args[1])) < 1e-9
+
+
+def test_density_fitting_factors_reproduce_the_integral_classes():
+    # the [df] formulas of the integral getters (ccsd_t.h:2210-2244 with is_df()) on the synthetic factors
+    p = make_problem(3, 5)
+    xab, xij, xai = p["x_ab"], p["x_ij"], p["x_ai"]
+    assert xab.shape == (p["naux"], 5, 5) and xij.shape == (p["naux"], 3, 3) and xai.shape == (p["naux"], 5, 3)
+    np.testing.assert_allclose(np.einsum("Kai,Kbj->abij", xai, xai), p["g_abij"], atol=1e-14)     # <ij|ab> = (ia|jb)
+    np.testing.assert_allclose(np.einsum("Kik,Kaj->aijk", xij, xai), p["g_aijk"], atol=1e-14)     # <ij|ka> = (ik|ja)
+    np.testing.assert_allclose(np.einsum("Kbi,Kac->abci", xai, xab), p["g_abci"], atol=1e-14)     # <ia|bc> = (ib|ac)
+    np.testing.assert_array_equal(xab, xab.transpose(0, 2, 1))
