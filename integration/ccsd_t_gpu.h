@@ -15,6 +15,9 @@
 
 #include <tiledarray.h>
 
+#include <cstdint>
+#include <cstdio>
+#include <string>
 #include <vector>
 
 #include "mpqc/chemistry/qc/lcao/cc/ccsd_t.h"
@@ -30,12 +33,16 @@ class CCSD_T_GPU : public CCSD_T<Tile, Policy> {
  public:
   using TArray = TA::DistArray<Tile, Policy>;
 
-  /// same keywords as CCSD_T plus: "ngpu" (devices per MPI rank, default 1), "gpu_batch" (0 = auto).
+  /// same keywords as CCSD_T plus: "ngpu" (devices per MPI rank, default 1), "gpu_batch" (0 = auto),
+  /// "gpu_dump_file" (write the dense (T) inputs for replay).  With a density-fitted CCSD (is_df()) the three
+  /// Xab/Xij/Xai factors (ccsd.h:480-493) can be passed through mpqc_t_energy_df instead of the dense
+  /// integrals (same call shape) so the v^3 o tensor is never gathered on the host.
   /// "approach" coarse|fine|straight all map to the GPU path (one exact sum); "laplace" stays on the CPU.
   explicit CCSD_T_GPU(const KeyVal &kv)
       : CCSD<Tile, Policy>(kv), CCSD_T<Tile, Policy>(kv),
         ngpu_(kv.value<int>("ngpu", 1)), gpu_batch_(kv.value<int>("gpu_batch", 0)),
-        laplace_(kv.value<std::string>("approach", "coarse") == "laplace") {}
+        laplace_(kv.value<std::string>("approach", "coarse") == "laplace"),
+        dump_file_(kv.value<std::string>("gpu_dump_file", "")) {}
 
  protected:
   /// gathers a (possibly sparse-policy, distributed) array into one dense row-major host buffer; zero tiles
@@ -64,6 +71,23 @@ class CCSD_T_GPU : public CCSD_T<Tile, Policy> {
     return out;
   }
 
+  /// writes the dense problem in the MPQCT001 dump format (mpqc_b200/dump.py reads it): lets a real-molecule (T)
+  /// be replayed where MPQC/Libint are not installed.  Enabled by the keyword "gpu_dump_file".
+  static void dump_t_problem(const std::string &path, const Eigen::VectorXd &eps, std::size_t n_frozen, std::size_t o,
+                             std::size_t v, const std::vector<double> &t1, const std::vector<double> &t2,
+                             const std::vector<double> &g_abij, const std::vector<double> &g_aijk,
+                             const std::vector<double> &g_abci) {
+    std::FILE *f = std::fopen(path.c_str(), "wb");
+    if (!f) throw FileOperationFailed("cannot open (T) dump file", __FILE__, __LINE__, path.c_str(),
+                                      FileOperationFailed::OpenW);
+    const int64_t hdr[4] = {int64_t(o), int64_t(v), int64_t(n_frozen), int64_t(n_frozen + o + v)};
+    std::fwrite("MPQCT001", 1, 8, f);
+    std::fwrite(hdr, sizeof(int64_t), 4, f);
+    std::fwrite(eps.data(), sizeof(double), n_frozen + o + v, f);
+    for (const auto *a : {&t1, &t2, &g_abij, &g_aijk, &g_abci}) std::fwrite(a->data(), sizeof(double), a->size(), f);
+    std::fclose(f);
+  }
+
   /// replaces CCSD_T::compute_ccsd_t (ccsd_t.h:144-177)
   void compute_ccsd_t_gpu() {
     auto &world = this->wfn_world()->world();
@@ -82,6 +106,9 @@ class CCSD_T_GPU : public CCSD_T<Tile, Policy> {
     std::vector<double> g_aijk = densify(this->get_aijk());
     std::vector<double> g_abci = densify(this->get_abci());
     const Eigen::VectorXd &eps = *this->orbital_energy();  // all MOs incl. frozen core (ccsd.h:141-148)
+
+    if (!dump_file_.empty() && world.rank() == 0)
+      dump_t_problem(dump_file_, eps, n_frozen, o, v, t1, t2, g_abij, g_aijk, g_abci);
 
     mpqc_t_problem p;
     p.o = static_cast<int64_t>(o);
@@ -147,6 +174,7 @@ class CCSD_T_GPU : public CCSD_T<Tile, Policy> {
   int ngpu_;
   int gpu_batch_;
   bool laplace_;
+  std::string dump_file_;
 };
 
 }  // namespace lcao

@@ -107,3 +107,22 @@ def test_two_rank_sharding_gloo():
     assert n_units == o * (o + 1) * (o + 2) // 6 - o
     for r in res:
         assert abs(r[2] - ref) < 1e-12
+
+
+def test_dump_roundtrip_and_h2o_fixture(tmp_path):
+    from mpqc_b200 import dump
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "h2o_631g.npz"))
+    path = str(tmp_path / "h2o.mpqct")
+    dump.save_problem(path, g["eps"], int(g["n_frozen"]), g["t1"], g["t2"], g["g_abij"], g["g_aijk"], g["g_abci"])
+    cc = dump.load_problem(path, e_ccsd=-1.0)
+    eng = cc.trange1_engine()
+    assert (eng.get_active_occ(), eng.get_vir(), eng.get_nfrozen()) == (4, 8, 1)
+    np.testing.assert_array_equal(cc.get_abci(), g["g_abci"])
+    np.testing.assert_array_equal(cc.orbital_energy(), g["eps"])
+    e = oc.ijk_driven(cc.t1(), cc.t2(), cc.get_abij(), cc.get_aijk(), cc.get_abci(), cc.orbital_energy()[1:5],
+                      cc.orbital_energy()[5:])
+    assert abs(e - (-0.000868413807153793)) < 1e-11
+    with open(path, "r+b") as f:
+        f.write(b"XXXX")
+    with pytest.raises(InputError):
+        dump.load_problem(path)
