@@ -96,3 +96,41 @@ def test_make_problem_validates_shapes():
     with pytest.raises(ValueError):
         L.make_problem(2, 3, p["eps_occ"], p["eps_vir"], p["t1"].astype(np.float32), p["t2"], p["g_abij"],
                        p["g_aijk"], p["g_abci"])
+
+
+def _build_c_host(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "c_host")
+    libdir = os.path.join(ROOT, "mpqc_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "c_host.c"), "-o", exe, "-L", libdir, "-lmpqc_t_cuda",
+                           f"-Wl,-rpath,{libdir}"])
+    return exe
+
+
+def _h2o_dump(tmp_path):
+    from mpqc_b200 import dump
+    g = np.load(os.path.join(ROOT, "tests", "golden", "h2o_631g.npz"))
+    path = str(tmp_path / "h2o.mpqct")
+    dump.save_problem(path, g["eps"], int(g["n_frozen"]), g["t1"], g["t2"], g["g_abij"], g["g_aijk"], g["g_abci"])
+    return path
+
+
+@pytest.mark.skipif(HAS_GPU, reason="CPU-box behaviour of the plain-C host")
+def test_plain_c_host_links_and_fails_loudly_without_gpu(lib, tmp_path):
+    # the header is consumable from C99 and the library from a C program; without a device: exit code 2
+    import subprocess
+    exe = _build_c_host(tmp_path)
+    res = subprocess.run([exe, _h2o_dump(tmp_path)], capture_output=True, text=True)
+    assert res.returncode == 2 and "no CPU fallback" in res.stderr
+
+
+@pytest.mark.gpu
+def test_plain_c_host_reproduces_reference_h2o(lib, tmp_path):
+    import subprocess
+    exe = _build_c_host(tmp_path)
+    res = subprocess.run([exe, _h2o_dump(tmp_path)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    e = float(res.stdout.split("E(T) =")[1].split()[0])
+    assert abs(e - (-0.000868413807153793)) < 1e-11
+    assert "(T) Energy:" in res.stdout

@@ -83,7 +83,7 @@ def _energy_oneshot(lib, p, **opts):
 # energy tile / the row patch / the 16-wide k-block) and the tiny edge cases
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("o,v", [(2, 1), (2, 3), (3, 8), (4, 9), (5, 16), (3, 17), (5, 19), (2, 31), (4, 40),
-                                 (11, 13), (6, 65), (3, 130)])
+                                 (11, 13), (9, 5), (6, 65), (3, 130)])
 def test_energy_matches_oracle(lib, o, v):
     p = make_problem(o, v, seed=1000 + 13 * o + v)
     e_gpu, st = _energy_oneshot(lib, p)
