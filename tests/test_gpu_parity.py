@@ -92,6 +92,30 @@ def test_energy_matches_oracle(lib, o, v):
     assert st.units == len(parts) and st.kernel_launches > 0
 
 
+@pytest.mark.parametrize("v", [48, 56, 64, 80, 88, 112, 120, 128, 136])
+def test_every_column_fragment_instantiation(lib, v):
+    # the W-contraction kernel is instantiated per column-fragment count NFRAG = 1..16; together with the ragged sizes
+    # above these cover all of them (v = 8*NFRAG for one column tile; 136 = two tiles of 9 with the last one short)
+    p = make_problem(2, v, seed=900 + v)
+    e_gpu, _ = _energy_oneshot(lib, p)
+    assert abs(e_gpu - oc.ijk_driven(*_args(p))) < TOL
+
+
+def test_scaled_down_twin_of_synthetic_config(lib):
+    # exact parity at a scaled-down twin (o=10, v=100) of the synthetic o=50, v=500 configuration
+    p = make_problem(10, 100, seed=555)
+    e_gpu, st = _energy_oneshot(lib, p)
+    assert st.units == 210
+    assert abs(e_gpu - oc.ijk_driven(*_args(p))) < TOL
+
+
+def test_v500_sampled_units(lib):
+    # v = 500 as in BASELINE.json's synthetic config (NFRAG = 16 tiles, four column tiles, last one short), with a small
+    # occupied space so that the inputs stay at 16 GB; two units against the oracle
+    n = lib.mpqc_t_triple_count(16)
+    assert _full_size_sample(lib, 16, 500, [7, n - 3], seed=15) < TOL
+
+
 def test_reference_default_approach_agrees(lib):
     # the reference's default 'coarse' loop (a>=b>=c blocks, CCSD_T_Reduce / ReduceSymm) on the same input
     p = make_problem(5, 21, seed=77)
