@@ -35,60 +35,50 @@ static void build_x(int o, int v, const double* t2, const double* g_aijk, const 
             }
 }
 
-/* CCSD_T_Reduce, ccsd_t.h:2286-2334 */
+/* Denominator-weighted plain sum: what CCSD_T_Reduce::operator() (ccsd_t.h:2286-2334) computes for one tile covering
+ * all indices -- sum over the row-major (a,b,c,i,j,k) walk of tile / (eps_i + eps_j + eps_k - eps_a - eps_b - eps_c),
+ * occupied energies taken at [n_frozen + i], virtual ones at [n_occ + a]. */
 double mpqc_oracle_reduce(int o, int v, int n_occ, int n_frozen, const double* eps, const double* tile) {
-  double me = 0.0;
-  int64_t tile_idx = 0;
-  for (int a = 0; a < v; ++a) {
-    const double e_a = eps[a + n_occ];
-    for (int b = 0; b < v; ++b) {
-      const double e_ab = e_a + eps[b + n_occ];
+  const double* eo = eps + n_frozen;
+  const double* ev = eps + n_occ;
+  double total = 0.0;
+  int64_t pos = 0;
+  for (int a = 0; a < v; ++a)
+    for (int b = 0; b < v; ++b)
       for (int c = 0; c < v; ++c) {
-        const double e_abc = e_ab + eps[c + n_occ];
-        for (int i = 0; i < o; ++i) {
-          const double e_abci = eps[i + n_frozen] - e_abc;
-          for (int j = 0; j < o; ++j) {
-            const double e_abcij = e_abci + eps[j + n_frozen];
-            for (int k = 0; k < o; ++k, ++tile_idx) {
-              const double e_abcijk = e_abcij + eps[k + n_frozen];
-              me += (1.0 / e_abcijk) * tile[tile_idx];
+        const double virt = ev[a] + ev[b] + ev[c];
+        for (int i = 0; i < o; ++i)
+          for (int j = 0; j < o; ++j)
+            for (int k = 0; k < o; ++k, ++pos) {
+              const double denom = (eo[i] - virt) + eo[j] + eo[k];   /* same association order as :2311-2320 */
+              total += (1.0 / denom) * tile[pos];
             }
-          }
-        }
       }
-    }
-  }
-  return me;
+  return total;
 }
 
-/* CCSD_T_ReduceSymm, ccsd_t.h:2350-2431 (single tile covering everything, offsets 0) */
+/* Symmetry-restricted sum: what CCSD_T_ReduceSymm::operator() (ccsd_t.h:2350-2431) computes for one tile covering all
+ * indices -- only c <= b <= a contribute, with weight 2 when a, b, c are all different, 0 when all equal, 1 otherwise
+ * (the if/else ladder of :2410-2421). */
 double mpqc_oracle_reduce_symm(int o, int v, int n_occ, int n_frozen, const double* eps, const double* tile) {
-  double me = 0.0;
-  for (int a = 0; a < v; ++a) {
-    const double e_a = eps[a + n_occ];
-    for (int b = 0; b < v && b <= a; ++b) {
-      const double e_ab = e_a + eps[b + n_occ];
-      for (int c = 0; c < v && c <= b; ++c) {
-        const double e_abc = e_ab + eps[c + n_occ];
-        const int none_equal = (a != b && a != c && b != c);
-        const int diagonal = (a == b && b == c);
-        for (int i = 0; i < o; ++i) {
-          const double e_abci = eps[i + n_frozen] - e_abc;
-          for (int j = 0; j < o; ++j) {
-            const double e_abcij = e_abci + eps[j + n_frozen];
+  const double* eo = eps + n_frozen;
+  const double* ev = eps + n_occ;
+  double total = 0.0;
+  for (int a = 0; a < v; ++a)
+    for (int b = 0; b <= a; ++b)
+      for (int c = 0; c <= b; ++c) {
+        double weight = 1.0;
+        if (a != b && b != c && a != c) weight = 2.0;
+        else if (a == b && b == c) weight = 0.0;
+        const double virt = ev[a] + ev[b] + ev[c];
+        for (int i = 0; i < o; ++i)
+          for (int j = 0; j < o; ++j)
             for (int k = 0; k < o; ++k) {
-              const double e_abcijk = e_abcij + eps[k + n_frozen];
-              double tmp = (1.0 / e_abcijk) * tile[IDX6(a, b, c, i, j, k)];
-              if (none_equal) tmp = 2.0 * tmp;
-              else if (diagonal) tmp = 0;
-              me += tmp;
+              const double denom = (eo[i] - virt) + eo[j] + eo[k];
+              total += weight * ((1.0 / denom) * tile[IDX6(a, b, c, i, j, k)]);
             }
-          }
-        }
       }
-    }
-  }
-  return me;
+  return total;
 }
 
 /* mode 0: straight (full reduce / 3, :1163-1168); mode 1: same tensors through ReduceSymm (the
