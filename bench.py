@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--e2e-units", type=int, default=2048, help="triples per GPU in the end-to-end (host buffer) call")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-blocks", type=int, default=2, help="(a,b,c) virtual-block triples in the CPU sample")
+    ap.add_argument("--cpu-blocks", type=int, default=8, help="(a,b,c) virtual-block triples in the CPU sample")
     return ap.parse_args()
 
 
@@ -98,14 +98,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
+def cpu_workers():
+    """Block-level worker threads x BLAS threads per worker for the CPU arm.  The reference spreads (a,b,c) block
+    triples over MPI ranks / MADNESS threads (ccsd_t.h:477-480); numpy's permutes and elementwise passes are
+    single-threaded, so the port gets its parallelism the same way: several block triples at once (numpy releases the
+    GIL), each with a share of the BLAS threads.  4 workers keeps a step of the trimer shape near 10 s and ~40 GB."""
+    cores = os.cpu_count() or 1
+    workers = 4 if cores >= 8 else max(1, cores // 2)
+    return workers, max(1, cores // workers)
+
+
 def cpu_sample(host: dict, o: int, v: int, nblocks: int, vir_block: int = 8):
     """Time the oracle port of the reference's default coarse (T) (ccsd_t.h:443-640) on a bounded sample of
-    strictly ordered (a>b>c) virtual-block triples; all host threads via numpy/OpenBLAS matmul."""
+    strictly ordered (a>b>c) virtual-block triples, `nblocks` of them, run concurrently on all host threads."""
+    from concurrent.futures import ThreadPoolExecutor
+    from threadpoolctl import threadpool_limits
     from oracle import ccsd_t_oracle as oc
     nb = (v + vir_block - 1) // vir_block
     # global_iter numbering of the a>=b>=c loop; pick strictly ordered full-size blocks spread over the range
     picks, it = [], 0
-    want = set()
     for a in range(nb):
         for b in range(a + 1):
             for c in range(b + 1):
@@ -115,10 +126,14 @@ def cpu_sample(host: dict, o: int, v: int, nblocks: int, vir_block: int = 8):
     if not picks:
         picks = list(range(1, it + 1))
     stride = max(1, len(picks) // nblocks)
-    want = set(picks[::stride][:nblocks])
+    want = picks[::stride][:nblocks]
     args = (host["t1"], host["t2"], host["g_abij"], host["g_aijk"], host["g_abci"], host["eps_occ"], host["eps_vir"])
+    workers, blas_threads = cpu_workers()
+    workers = min(workers, len(want))
     t0 = time.perf_counter()
-    oc.coarse(*args, vir_block=vir_block, block_filter=want)
+    with threadpool_limits(limits=max(1, (os.cpu_count() or 1) // workers)):
+        with ThreadPoolExecutor(workers) as ex:
+            list(ex.map(lambda g: oc.coarse(*args, vir_block=vir_block, block_filter={g}), want))
     dt = time.perf_counter() - t0
     fl = len(want) * 12.0 * vir_block ** 3 * float(o) ** 3 * (v + o)
     return fl / dt * 1e-12, dt, len(want)
@@ -164,15 +179,14 @@ def run_reference(args):
         from mpqc_b200.synthetic import make_problem
         host = make_problem(o, v)
     cores = os.cpu_count()
+    workers, blas_threads = cpu_workers()
     for _ in range(args.warmup):
-        cpu_sample(host, o, v, 1)
+        cpu_sample(host, o, v, workers)
     t0 = time.perf_counter()
-    tf_sum, n = 0.0, 0
     fl_total = 0.0
     for _ in range(args.steps):
-        tf, dt, nblk = cpu_sample(host, o, v, 1)
+        tf, dt, nblk = cpu_sample(host, o, v, workers)
         fl_total += tf * dt
-        n += 1
     wall = time.perf_counter() - t0
     value = fl_total / wall
     line = {
@@ -181,10 +195,11 @@ def run_reference(args):
         "ms_per_step": wall / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload}: o={o}, v={v} ({desc})",
-                   "step": "one strictly ordered (a>b>c) virtual-block triple (block 8) of the reference's coarse loop"},
+                   "step": f"{workers} strictly ordered (a>b>c) virtual-block triples (block 8) of the reference's coarse "
+                           f"loop, run concurrently ({workers} workers x {blas_threads} BLAS threads)"},
         "cpu_baseline": {"value": value, "unit": "TFLOP/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps x 1 (a>b>c) block triple (vir block 8) of ccsd_t.h:443-640, "
-                                   "numpy/OpenBLAS matmul, all host threads"},
+                         "sample": f"{args.steps} steps x {workers} (a>b>c) block triples (vir block 8) of ccsd_t.h:443-640, "
+                                   f"numpy/OpenBLAS, {workers} concurrent block workers x {blas_threads} BLAS threads"},
         "e2e": {"value": value, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -364,7 +379,8 @@ def run_ours(args):
         tf, dt, nblk = cpu_sample(as_numpy(host), o, v, args.cpu_blocks)
         cpu = {"value": tf, "unit": "TFLOP/s", "cores": os.cpu_count(), "kind": "port",
                "sample": f"{nblk} strictly ordered (a>b>c) virtual-block triples (block 8) of the reference's coarse loop "
-                         f"(ccsd_t.h:443-640) on the same o={o}, v={v} inputs, numpy/OpenBLAS, {dt:.1f} s"}
+                         f"(ccsd_t.h:443-640) on the same o={o}, v={v} inputs, numpy/OpenBLAS, "
+                         f"{cpu_workers()[0]} concurrent block workers x {cpu_workers()[1]} BLAS threads, {dt:.1f} s"}
 
     if rank == 0:
         line = {
