@@ -1,3 +1,4 @@
+"""Developer tool (not product code): uses the oracle only as the checker."""
 """Tiny end-to-end run for compute-sanitizer (memcheck / racecheck / synccheck)."""
 import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
