@@ -34,6 +34,7 @@ WORKLOADS = {
     "benzene-cc-pVDZ": (21, 93, "benzene CCSD(T)/cc-pVDZ shape"),
     "water10-cc-pVTZ": (40, 530, "(H2O)10 CCSD(T)/cc-pVTZ shape"),
     "synthetic-o50-v500": (50, 500, "synthetic random T2/integrals"),
+    "tiny-selftest": (12, 40, "tiny shape for the CPU self-test of this script (tests/test_host_logic.py)"),
 }
 FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 * 1e-12     # 148 SMs x 64 DFMA/clk x 1.965 GHz = 37.2
 

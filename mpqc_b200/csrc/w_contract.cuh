@@ -38,7 +38,10 @@ namespace mpqc_t {
 constexpr int kBM = 128;           // rows of a CTA tile (8 consumer warps x 16)
 constexpr int kBK = 16;            // doubles per k-block = one 128-byte swizzled row
 constexpr int kMaxNFrag = 16;      // 8-column fragments per tile -> tn <= 128
-constexpr int kStages = 5;
+#ifndef MPQC_T_STAGES
+#define MPQC_T_STAGES 5
+#endif
+constexpr int kStages = MPQC_T_STAGES;
 constexpr int kConsumerWarps = 8;
 constexpr int kGemmThreads = (kConsumerWarps + 4) * 32;   // 2 consumer warpgroups + 1 producer warpgroup
 constexpr int kAStageBytes = kBM * kBK * 8;              // 16 KB

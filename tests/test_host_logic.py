@@ -138,3 +138,22 @@ def test_adapter_header_compiles_against_mocks():
                           os.path.join(root, "integration"), "-I", os.path.join(root, "include"),
                           os.path.join(mock, "check_adapter.cpp")], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
+
+
+def test_bench_reference_arm_json_contract():
+    # the CPU arm of bench.py on a tiny shape: one JSON line with the keys the driver reads
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload",
+                          "tiny-selftest", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, env=env,
+                         timeout=300)
+    assert res.returncode == 0, res.stderr
+    line = json.loads([x for x in res.stdout.splitlines() if x.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["unit"] == "TFLOP/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["dtype"] == "f64" and line["vs_baseline"] is None
+    assert set(line["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"] and "model" not in line["config"]
