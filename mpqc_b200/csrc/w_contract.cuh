@@ -12,7 +12,7 @@
 // 6-index permutes of ccsd_t.h:498-555 never touch HBM).
 //
 // Machine mapping (sm_100a): persistent grid, one CTA per SM, three warpgroups.  One producer lane
-// issues TMA (cp.async.bulk.tensor, 128B-swizzled boxes) into a kStages-deep shared-memory ring guarded
+// issues TMA (cp.async.bulk.tensor, 128B-swizzled boxes) into a kStages-deep shared-memory ring (two k-blocks per stage) guarded
 // by full/empty mbarriers; eight consumer warps each own a 16-row x (8*NFRAG)-column slice of the
 // 128 x tn output tile and issue FP64 tensor-core DMMA.8x8x4 from conflict-free LDS.128 fragment reads.
 // tcgen05/TMEM has no FP64 kind, so DMMA is the Blackwell tensor path for doubles.
@@ -38,15 +38,17 @@ namespace mpqc_t {
 constexpr int kBM = 128;           // rows of a CTA tile (8 consumer warps x 16)
 constexpr int kBK = 16;            // doubles per k-block = one 128-byte swizzled row
 constexpr int kMaxNFrag = 16;      // 8-column fragments per tile -> tn <= 128
+constexpr int kSub = 2;             // k-blocks per pipeline stage: one full/empty barrier round trip per 32 kap
 #ifndef MPQC_T_STAGES
-#define MPQC_T_STAGES 5
+#define MPQC_T_STAGES 3
 #endif
 constexpr int kStages = MPQC_T_STAGES;
 constexpr int kConsumerWarps = 8;
 constexpr int kGemmThreads = (kConsumerWarps + 4) * 32;   // 2 consumer warpgroups + 1 producer warpgroup
-constexpr int kAStageBytes = kBM * kBK * 8;              // 16 KB
-constexpr int kBStageBytes = kMaxNFrag * 8 * kBK * 8;    // 16 KB
-constexpr int kStageBytes = kAStageBytes + kBStageBytes;
+constexpr int kAStageBytes = kBM * kBK * 8;              // 16 KB  (A rows of one k-block)
+constexpr int kBStageBytes = kMaxNFrag * 8 * kBK * 8;    // 16 KB  (B rows of one k-block)
+constexpr int kSubBytes = kAStageBytes + kBStageBytes;   // one k-block
+constexpr int kStageBytes = kSub * kSubBytes;            // 64 KB
 constexpr int kGemmSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 struct GemmParams {
@@ -152,11 +154,12 @@ struct ConsumerRegs {
 };
 
 // One k-block.  On entry R holds the A fragments and B chunk 0 (in bb[0]) of this block.  On exit, if
-// has_next, it holds those of the next block (read from stage `ns` after waiting on its full barrier).
+// has_next, it holds those of the next block (read from its stage slot, after waiting on that stage's full
+// barrier when the next block is the first of a new stage).
 template <int NFRAG, bool HALF, int SKIP>
 __device__ __forceinline__ void kblock(double (&acc)[2][NFRAG][2], ConsumerRegs<NFRAG>& R, uint32_t sb_cur,
-                                       bool has_next, uint64_t* next_full, uint32_t next_phase, uint32_t sa_next,
-                                       uint32_t a0_next, uint32_t a1_next, uint32_t sb_next) {
+                                       bool has_next, bool need_wait, uint64_t* next_full, uint32_t next_phase,
+                                       uint32_t sa_next, uint32_t a0_next, uint32_t a1_next, uint32_t sb_next) {
   using CH = Chunking<NFRAG>;
   double2 nlo[2], nhi[2];
 #pragma unroll
@@ -170,7 +173,7 @@ __device__ __forceinline__ void kblock(double (&acc)[2][NFRAG][2], ConsumerRegs<
       if (c == 4) load_b_chunk<NFRAG, (5 < CH::kNum ? 5 : 0)>(R.bb[1], sb_cur);
     } else if (has_next) {
       // last chunk: fetch the next k-block's A fragments and B chunk 0 before issuing this chunk's DMMAs
-      mbar_wait(next_full, next_phase);
+      if (need_wait) mbar_wait(next_full, next_phase);   // the next k-block opens a new pipeline stage
       nlo[0] = lds128(sa_next + a0_next);
       nlo[1] = lds128(sa_next + a1_next);
       nhi[0] = lds128(sa_next + (a0_next ^ 64u));
@@ -200,7 +203,7 @@ __device__ __forceinline__ void kblock(double (&acc)[2][NFRAG][2], ConsumerRegs<
 // Consumer tile loop for tiles [tile, tile_end) of this CTA (stride gridDim.x); SKIP as in mma_chunk.
 template <int NFRAG, int SKIP>
 __device__ __forceinline__ void consume_tiles(const GemmParams& P, int& tile, const int tile_end, ConsumerRegs<NFRAG>& R,
-                                              int& stage, uint32_t& phase, uint64_t* full_bar, uint64_t* empty_bar,
+                                              int& stage, uint32_t& phase, int& sub, uint64_t* full_bar, uint64_t* empty_bar,
                                               const uint32_t smem_base, const uint32_t b_lo_off,
                                               const uint32_t (&a_off_n)[2], const uint32_t (&a_off_t)[2], const int warp,
                                               const int lane, const int sg, const int kq) {
@@ -217,23 +220,32 @@ __device__ __forceinline__ void consume_tiles(const GemmParams& P, int& tile, co
 
     for (int q = 0; q < nblk; ++q) {
       const bool last_in_tile = (q == nblk - 1);
+      const bool last_in_term = (q == kblocks - 1) || last_in_tile;
       const bool has_next = !last_in_tile || more_tiles;
       const bool next_transposed = !last_in_tile && (q + 1 >= kblocks);
-      const int ns = (stage + 1 == kStages) ? 0 : stage + 1;
-      const uint32_t nph = (ns == 0) ? (phase ^ 1u) : phase;
-      const uint32_t sa_next = smem_base + ns * kStageBytes;
+      // the next k-block lives in the other half of this stage, or opens the next stage
+      const bool new_stage = last_in_term || (sub == kSub - 1);
+      const int ns = new_stage ? ((stage + 1 == kStages) ? 0 : stage + 1) : stage;
+      const uint32_t nph = (new_stage && ns == 0) ? (phase ^ 1u) : phase;
+      const int nsub = new_stage ? 0 : sub + 1;
+      const uint32_t sa_next = smem_base + ns * kStageBytes + nsub * kSubBytes;
       const uint32_t a0n = next_transposed ? a_off_t[0] : a_off_n[0];
       const uint32_t a1n = next_transposed ? a_off_t[1] : a_off_n[1];
-      const uint32_t sb_cur = smem_base + stage * kStageBytes + b_lo_off;
+      const uint32_t sb_cur = smem_base + stage * kStageBytes + sub * kSubBytes + b_lo_off;
       const bool half = half_last && (q == kblocks - 1 || q == nblk - 1);
       if (half)
-        kblock<NFRAG, true, SKIP>(acc, R, sb_cur, has_next, &full_bar[ns], nph, sa_next, a0n, a1n, sa_next + b_lo_off);
+        kblock<NFRAG, true, SKIP>(acc, R, sb_cur, has_next, new_stage, &full_bar[ns], nph, sa_next, a0n, a1n,
+                                  sa_next + b_lo_off);
       else
-        kblock<NFRAG, false, SKIP>(acc, R, sb_cur, has_next, &full_bar[ns], nph, sa_next, a0n, a1n, sa_next + b_lo_off);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        kblock<NFRAG, false, SKIP>(acc, R, sb_cur, has_next, new_stage, &full_bar[ns], nph, sa_next, a0n, a1n,
+                                   sa_next + b_lo_off);
+      if (new_stage) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      }
       stage = ns;
       phase = nph;
+      sub = nsub;
     }
 
     // ---- epilogue: registers -> N_g[p][q][r0 + col] (32-byte sector-aligned runs) ----
@@ -317,19 +329,23 @@ w_contract_dmma_kernel(const __grid_constant__ CUtensorMap tmA_n,   // patch: A 
         else             { x1 = k; yz1 = j * P.o + i; x2 = j; yz2 = k * P.o + i; }
         const int p0 = (mt / P.nqt) * P.tp, q0 = (mt % P.nqt) * P.tq, r0 = nt * P.tn, m0 = mt * kBM;
         for (int term = 0; term < 2; ++term) {
-          for (int kb = 0; kb < P.kblocks; ++kb) {
+          for (int kb = 0; kb < P.kblocks; kb += kSub) {
+            const int nsub = (P.kblocks - kb) < kSub ? (P.kblocks - kb) : kSub;
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + stage * kStageBytes;
-            uint8_t* sb = sa + kAStageBytes;
-            mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
-            if (term == 0) {
-              if (P.flat) tma_load_3d(sa, &tmA_n, &full_bar[stage], kb * kBK, m0, x1);
-              else        tma_load_4d(sa, &tmA_n, &full_bar[stage], kb * kBK, q0, p0, x1);
-              tma_load_3d(sb, &tmB, &full_bar[stage], kb * kBK, r0, yz1);
-            } else {
-              if (P.flat) tma_load_3d(sa, &tmA_t, &full_bar[stage], kb * kBK, m0, x2);
-              else        tma_load_4d(sa, &tmA_t, &full_bar[stage], kb * kBK, p0, q0, x2);
-              tma_load_3d(sb, &tmB, &full_bar[stage], kb * kBK, r0, yz2);
+            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)nsub * (a_bytes + b_bytes));
+            for (int sub = 0; sub < nsub; ++sub) {
+              uint8_t* sa = smem + stage * kStageBytes + sub * kSubBytes;
+              uint8_t* sb = sa + kAStageBytes;
+              const int kap0 = (kb + sub) * kBK;
+              if (term == 0) {
+                if (P.flat) tma_load_3d(sa, &tmA_n, &full_bar[stage], kap0, m0, x1);
+                else        tma_load_4d(sa, &tmA_n, &full_bar[stage], kap0, q0, p0, x1);
+                tma_load_3d(sb, &tmB, &full_bar[stage], kap0, r0, yz1);
+              } else {
+                if (P.flat) tma_load_3d(sa, &tmA_t, &full_bar[stage], kap0, m0, x2);
+                else        tma_load_4d(sa, &tmA_t, &full_bar[stage], kap0, p0, q0, x2);
+                tma_load_3d(sb, &tmB, &full_bar[stage], kap0, r0, yz2);
+              }
             }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
@@ -359,7 +375,7 @@ w_contract_dmma_kernel(const __grid_constant__ CUtensorMap tmA_n,   // patch: A 
     int srow = P.flat ? m : (mm % P.tq) * P.tp + (mm / P.tq);   // row of (p,q) inside the term-1 box
     a_off_t[mi] = (uint32_t)srow * 128u + (uint32_t)((kq ^ (srow & 7)) << 4);
   }
-  int stage = 0;
+  int stage = 0, sub = 0;
   uint32_t phase = 0;
   ConsumerRegs<NFRAG> R;
   if ((int)blockIdx.x < P.total_tiles) {
@@ -372,9 +388,9 @@ w_contract_dmma_kernel(const __grid_constant__ CUtensorMap tmA_n,   // patch: A 
     load_b_chunk<NFRAG, 0>(R.bb[0], smem_base + b_lo_off);
   }
   int tile = blockIdx.x;
-  consume_tiles<NFRAG, 0>(P, tile, P.main_tiles, R, stage, phase, full_bar, empty_bar, smem_base, b_lo_off, a_off_n,
+  consume_tiles<NFRAG, 0>(P, tile, P.main_tiles, R, stage, phase, sub, full_bar, empty_bar, smem_base, b_lo_off, a_off_n,
                           a_off_t, warp, lane, sg, kq);
-  consume_tiles<NFRAG, (NFRAG >= 2 ? 1 : 0)>(P, tile, P.total_tiles, R, stage, phase, full_bar, empty_bar, smem_base,
+  consume_tiles<NFRAG, (NFRAG >= 2 ? 1 : 0)>(P, tile, P.total_tiles, R, stage, phase, sub, full_bar, empty_bar, smem_base,
                                             b_lo_off, a_off_n, a_off_t, warp, lane, sg, kq);
 }
 
