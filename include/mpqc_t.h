@@ -152,7 +152,8 @@ const char* mpqc_t_strerror(int status);
 const char* mpqc_t_last_error(void);                 /* thread-local detail string of the last failure */
 
 /* FP64 pipe microbenchmarks used to fix the roofline denominator on the box:
- * which = 0: DMMA.8x8x4 issue-bound loop, 1: DFMA issue-bound loop.  Returns TFLOP/s in *tflops. */
+ * which = 0: DMMA.8x8x4 issue-bound loop (32 warps/SM), 1: DFMA issue-bound loop, 2: DMMA loop at the W-contraction
+ * kernel's occupancy (8 warps/SM, two per scheduler).  Returns TFLOP/s in *tflops. */
 int mpqc_t_microbench(int32_t device, int32_t which, double* tflops);
 
 #ifdef __cplusplus

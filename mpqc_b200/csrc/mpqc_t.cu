@@ -1148,14 +1148,15 @@ int mpqc_t_microbench(int32_t device, int32_t which, double* tflops) {
   MPQC_T_CUDA(cudaGetDeviceProperties(&prop, device));
   double* out = nullptr;
   MPQC_T_CUDA(cudaMalloc(&out, 64));
-  const int blocks = prop.multiProcessorCount * 4, threads = 256, iters = 20000;
+  // which = 2: DMMA with ONE 8-warp block per SM (two warps per scheduler, the W-contraction kernel's occupancy)
+  const int blocks = prop.multiProcessorCount * (which == 2 ? 1 : 4), threads = 256, iters = 20000;
   cudaEvent_t e0, e1;
   MPQC_T_CUDA(cudaEventCreate(&e0));
   MPQC_T_CUDA(cudaEventCreate(&e1));
   float best = 1e30f;
   for (int rep = 0; rep < 4; ++rep) {
     cudaEventRecord(e0);
-    if (which == 0) microbench_dmma_kernel<<<blocks, threads>>>(out, iters);
+    if (which == 0 || which == 2) microbench_dmma_kernel<<<blocks, threads>>>(out, iters);
     else microbench_dfma_kernel<<<blocks, threads>>>(out, iters);
     cudaEventRecord(e1);
     MPQC_T_CUDA(cudaEventSynchronize(e1));
@@ -1165,7 +1166,7 @@ int mpqc_t_microbench(int32_t device, int32_t which, double* tflops) {
   }
   MPQC_T_CUDA(cudaGetLastError());
   double fl;
-  if (which == 0) fl = (double)blocks * (threads / 32) * (double)iters * 8.0 * 512.0;
+  if (which == 0 || which == 2) fl = (double)blocks * (threads / 32) * (double)iters * 8.0 * 512.0;
   else fl = (double)blocks * threads * (double)iters * 8.0 * 2.0;
   *tflops = fl / (best * 1e-3) * 1e-12;
   cudaEventDestroy(e0);
