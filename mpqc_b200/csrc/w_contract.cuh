@@ -200,6 +200,50 @@ __device__ __forceinline__ void kblock(double (&acc)[2][NFRAG][2], ConsumerRegs<
   }
 }
 
+// TMA producer (one elected lane of the producer warpgroup): walks this CTA's tiles and streams, per pipeline stage,
+// kSub k-blocks of the A rows and the B rows into the shared-memory ring.
+__device__ __forceinline__ void producer_loop(const GemmParams& P, const CUtensorMap* tmA_n, const CUtensorMap* tmA_t,
+                                              const CUtensorMap* tmB, uint8_t* smem, uint64_t* full_bar,
+                                              uint64_t* empty_bar, const uint32_t a_bytes, const uint32_t b_bytes) {
+      tma_prefetch_desc(tmA_n);
+      tma_prefetch_desc(tmA_t);
+      tma_prefetch_desc(tmB);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        int b, g, mt, nt;
+        decode_tile(P, tile, b, g, mt, nt);
+        const int i = P.triples[3 * b + 0], j = P.triples[3 * b + 1], k = P.triples[3 * b + 2];
+        int x1, yz1, x2, yz2;
+        if (g == 0)      { x1 = i; yz1 = j * P.o + k; x2 = j; yz2 = i * P.o + k; }
+        else if (g == 1) { x1 = i; yz1 = k * P.o + j; x2 = k; yz2 = i * P.o + j; }
+        else             { x1 = k; yz1 = j * P.o + i; x2 = j; yz2 = k * P.o + i; }
+        const int p0 = (mt / P.nqt) * P.tp, q0 = (mt % P.nqt) * P.tq, r0 = nt * P.tn, m0 = mt * kBM;
+        for (int term = 0; term < 2; ++term) {
+          for (int kb = 0; kb < P.kblocks; kb += kSub) {
+            const int nsub = (P.kblocks - kb) < kSub ? (P.kblocks - kb) : kSub;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)nsub * (a_bytes + b_bytes));
+            for (int sub = 0; sub < nsub; ++sub) {
+              uint8_t* sa = smem + stage * kStageBytes + sub * kSubBytes;
+              uint8_t* sb = sa + kAStageBytes;
+              const int kap0 = (kb + sub) * kBK;
+              if (term == 0) {
+                if (P.flat) tma_load_3d(sa, tmA_n, &full_bar[stage], kap0, m0, x1);
+                else        tma_load_4d(sa, tmA_n, &full_bar[stage], kap0, q0, p0, x1);
+                tma_load_3d(sb, tmB, &full_bar[stage], kap0, r0, yz1);
+              } else {
+                if (P.flat) tma_load_3d(sa, tmA_t, &full_bar[stage], kap0, m0, x2);
+                else        tma_load_4d(sa, tmA_t, &full_bar[stage], kap0, p0, q0, x2);
+                tma_load_3d(sb, tmB, &full_bar[stage], kap0, r0, yz2);
+              }
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+}
+
 // Consumer tile loop for tiles [tile, tile_end) of this CTA (stride gridDim.x); SKIP as in mma_chunk.
 template <int NFRAG, int SKIP>
 __device__ __forceinline__ void consume_tiles(const GemmParams& P, int& tile, const int tile_end, ConsumerRegs<NFRAG>& R,
@@ -313,45 +357,7 @@ w_contract_dmma_kernel(const __grid_constant__ CUtensorMap tmA_n,   // patch: A 
     // hand the producer warpgroup's registers to the consumers (each SMSP's 16K-entry file holds
     // two consumer warps + one producer-group warp: 2*232 + 40 <= 512)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp == kConsumerWarps && lane == 0) {
-      tma_prefetch_desc(&tmA_n);
-      tma_prefetch_desc(&tmA_t);
-      tma_prefetch_desc(&tmB);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        int b, g, mt, nt;
-        decode_tile(P, tile, b, g, mt, nt);
-        const int i = P.triples[3 * b + 0], j = P.triples[3 * b + 1], k = P.triples[3 * b + 2];
-        int x1, yz1, x2, yz2;
-        if (g == 0)      { x1 = i; yz1 = j * P.o + k; x2 = j; yz2 = i * P.o + k; }
-        else if (g == 1) { x1 = i; yz1 = k * P.o + j; x2 = k; yz2 = i * P.o + j; }
-        else             { x1 = k; yz1 = j * P.o + i; x2 = j; yz2 = k * P.o + i; }
-        const int p0 = (mt / P.nqt) * P.tp, q0 = (mt % P.nqt) * P.tq, r0 = nt * P.tn, m0 = mt * kBM;
-        for (int term = 0; term < 2; ++term) {
-          for (int kb = 0; kb < P.kblocks; kb += kSub) {
-            const int nsub = (P.kblocks - kb) < kSub ? (P.kblocks - kb) : kSub;
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)nsub * (a_bytes + b_bytes));
-            for (int sub = 0; sub < nsub; ++sub) {
-              uint8_t* sa = smem + stage * kStageBytes + sub * kSubBytes;
-              uint8_t* sb = sa + kAStageBytes;
-              const int kap0 = (kb + sub) * kBK;
-              if (term == 0) {
-                if (P.flat) tma_load_3d(sa, &tmA_n, &full_bar[stage], kap0, m0, x1);
-                else        tma_load_4d(sa, &tmA_n, &full_bar[stage], kap0, q0, p0, x1);
-                tma_load_3d(sb, &tmB, &full_bar[stage], kap0, r0, yz1);
-              } else {
-                if (P.flat) tma_load_3d(sa, &tmA_t, &full_bar[stage], kap0, m0, x2);
-                else        tma_load_4d(sa, &tmA_t, &full_bar[stage], kap0, p0, q0, x2);
-                tma_load_3d(sb, &tmB, &full_bar[stage], kap0, r0, yz2);
-              }
-            }
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
-    }
+    if (warp == kConsumerWarps && lane == 0) producer_loop(P, &tmA_n, &tmA_t, &tmB, smem, full_bar, empty_bar, a_bytes, b_bytes);
     return;
   }
 
