@@ -333,20 +333,25 @@ def run_ours(args):
         h = None
         del pd
         torch.cuda.empty_cache()
-        barrier()
-        est = L.Stats()
-        e = C.c_double()
-        t0 = time.perf_counter()
-        L.check(lib.mpqc_t_energy(C.byref(hp), C.byref(opt), C.byref(e), C.byref(est)), "mpqc_t_energy")
-        if world > 1:
-            t = torch.tensor([e.value], dtype=torch.float64, device=f"cuda:{local}")
-            dist.all_reduce(t)
-        torch.cuda.synchronize()
-        ewall = time.perf_counter() - t0
-        tt = torch.tensor([ewall], dtype=torch.float64, device=f"cuda:{local}")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ewall = float(tt.cpu()[0])
+        # two identical calls: the first is the warm-up of this path (first large cudaMalloc after torch released its
+        # pool, first touch of the pinned pages), the second is the one reported; both durations are in the JSON
+        ewalls = []
+        for _rep in range(2):
+            barrier()
+            est = L.Stats()
+            e = C.c_double()
+            t0 = time.perf_counter()
+            L.check(lib.mpqc_t_energy(C.byref(hp), C.byref(opt), C.byref(e), C.byref(est)), "mpqc_t_energy")
+            if world > 1:
+                t = torch.tensor([e.value], dtype=torch.float64, device=f"cuda:{local}")
+                dist.all_reduce(t)
+            torch.cuda.synchronize()
+            ewall = time.perf_counter() - t0
+            tt = torch.tensor([ewall], dtype=torch.float64, device=f"cuda:{local}")
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ewalls.append(float(tt.cpu()[0]))
+        ewall = ewalls[-1]
         esteps = EU / U
         # same call with the density-fitting factors in place of the dense integrals: the
         # v^3 o tensor is assembled on the device, so ~6x fewer bytes cross PCIe
@@ -368,7 +373,8 @@ def run_ours(args):
                   "call": "mpqc_t_energy_df(host buffers): t2 + three-centre factors cross PCIe, integrals assembled on device"}
         e2e = {"value": EU * n_gpus * unit_flops / ewall * 1e-12, "unit": "TFLOP/s",
                "h2d_bytes_per_step": est.bytes_h2d / esteps, "d2h_bytes_per_step": est.bytes_d2h / esteps,
-               "units_per_gpu": EU, "seconds": ewall, "seconds_upload": est.seconds_upload,
+               "units_per_gpu": EU, "seconds": ewall, "seconds_warmup_call": ewalls[0],
+               "seconds_upload": est.seconds_upload,
                "seconds_relayout": est.seconds_relayout, "seconds_compute": est.seconds_compute,
                "call": "mpqc_t_energy(host buffers) = H2D of all inputs + relayout + triples + D2H of unit energies"}
 
