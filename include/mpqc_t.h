@@ -151,6 +151,22 @@ const char* mpqc_t_version(void);
 const char* mpqc_t_strerror(int status);
 const char* mpqc_t_last_error(void);                 /* thread-local detail string of the last failure */
 
+/* Host-only: the tiling plan the W-contraction kernel would use for (o, v) -- row mode, tile counts, column-fragment
+ * count -- and the resulting fraction of executed tensor-core FLOPs that are algorithmic.  No device is touched. */
+typedef struct mpqc_t_plan_info {
+  int64_t kp;            /* padded contraction length roundup8(v+o) (>= 16) */
+  int32_t flat;          /* 1: flattened (p,q) rows + transposed operand copy; 0: (tp x tq) row patches */
+  int32_t tp, tq;        /* row patch (patch mode) */
+  int32_t row_tiles;     /* 128-row tiles per group */
+  int32_t col_tiles;     /* column tiles */
+  int32_t nfrag;         /* 8-column fragments per column tile (kernel instantiation) */
+  int32_t skip_last;     /* 1: the last column tile drops its trailing fragment */
+  int32_t energy_tile_sets; /* blocks per triple of the energy kernel */
+  double flop_efficiency;   /* 12 v^3 (v+o) / executed FLOPs per triple */
+  double bytes_operands;    /* resident operand bytes (A [+AT], B, GV) */
+} mpqc_t_plan_info;
+int mpqc_t_plan(int64_t o, int64_t v, int32_t flat, mpqc_t_plan_info* out);
+
 /* FP64 pipe microbenchmarks used to fix the roofline denominator on the box:
  * which = 0: DMMA.8x8x4 issue-bound loop (32 warps/SM), 1: DFMA issue-bound loop, 2: DMMA loop at the W-contraction
  * kernel's occupancy (8 warps/SM, two per scheduler).  Returns TFLOP/s in *tflops. */

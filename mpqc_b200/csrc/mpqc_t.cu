@@ -714,6 +714,32 @@ int mpqc_t_triple_of_unit(int64_t o, int64_t unit, int32_t* i, int32_t* j, int32
 double mpqc_t_flops(int64_t o, int64_t v) { return 2.0 * (double)o * o * o * (double)v * v * v * (double)(v + o); }
 double mpqc_t_unit_flops(int64_t o, int64_t v) { return 12.0 * (double)v * v * v * (double)(v + o); }
 
+int mpqc_t_plan(int64_t o, int64_t v, int32_t flat, mpqc_t_plan_info* out) {
+  MPQC_T_CHECK(out != nullptr, MPQC_T_ERR_BAD_ARG, "plan output is NULL");
+  MPQC_T_CHECK(o >= 1 && v >= 1 && o <= 4096 && v <= 2040, MPQC_T_ERR_BAD_ARG, "need 1 <= o <= 4096, 1 <= v <= 2040");
+  mpqc_t_handle h;                       // host-side fields only; no device call is made
+  h.o = o;
+  h.v = v;
+  h.Kp = std::max<int64_t>(16, roundup(v + o, 8));
+  h.flat = flat != 0;
+  MPQC_T_TRY(plan(&h));
+  memset(out, 0, sizeof(*out));
+  out->kp = h.Kp;
+  out->flat = h.flat;
+  out->tp = h.tp;
+  out->tq = h.tq;
+  out->row_tiles = h.nmt;
+  out->col_tiles = h.nnt;
+  out->nfrag = h.nfrag;
+  out->skip_last = h.skip_last;
+  out->energy_tile_sets = h.ntt;
+  const double mpad = (double)h.nmt * kBM, npad = (double)h.nnt * h.tn - 8.0 * h.skip_last;
+  out->flop_efficiency = mpqc_t_unit_flops(o, v) / (3.0 * 2.0 * 2.0 * mpad * npad * (double)h.Kp);
+  const double a = (double)o * v * v * h.Kp * 8.0;
+  out->bytes_operands = a * (h.flat ? 2.0 : 1.0) + (double)o * o * v * h.Kp * 8.0 + (double)o * o * v * v * 8.0;
+  return MPQC_T_OK;
+}
+
 int mpqc_t_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) {

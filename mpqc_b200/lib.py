@@ -30,6 +30,12 @@ class DfProblem(C.Structure):
                 ("x_ab", C.c_void_p), ("x_ij", C.c_void_p), ("x_ai", C.c_void_p)]
 
 
+class PlanInfo(C.Structure):
+    _fields_ = [("kp", C.c_int64), ("flat", C.c_int32), ("tp", C.c_int32), ("tq", C.c_int32), ("row_tiles", C.c_int32),
+                ("col_tiles", C.c_int32), ("nfrag", C.c_int32), ("skip_last", C.c_int32), ("energy_tile_sets", C.c_int32),
+                ("flop_efficiency", C.c_double), ("bytes_operands", C.c_double)]
+
+
 class Options(C.Structure):
     _fields_ = [("ngpu", C.c_int32), ("device_ids", C.POINTER(C.c_int32)), ("verbose", C.c_int32),
                 ("inputs_on_device", C.c_int32), ("unit_first", C.c_int64), ("unit_stride", C.c_int64),
@@ -58,7 +64,7 @@ class MpqcTError(RuntimeError):
 SYMBOLS = [
     "mpqc_t_energy", "mpqc_t_energy_df", "mpqc_t_create", "mpqc_t_upload", "mpqc_t_upload_df", "mpqc_t_run", "mpqc_t_debug_w", "mpqc_t_stream",
     "mpqc_t_destroy", "mpqc_t_triple_count", "mpqc_t_triple_of_unit", "mpqc_t_flops", "mpqc_t_unit_flops",
-    "mpqc_t_device_count", "mpqc_t_version", "mpqc_t_strerror", "mpqc_t_last_error", "mpqc_t_microbench",
+    "mpqc_t_device_count", "mpqc_t_plan", "mpqc_t_version", "mpqc_t_strerror", "mpqc_t_last_error", "mpqc_t_microbench",
 ]
 
 _lib = None
@@ -102,6 +108,8 @@ def load() -> C.CDLL:
     lib.mpqc_t_flops.restype = C.c_double
     lib.mpqc_t_unit_flops.argtypes = [C.c_int64, C.c_int64]
     lib.mpqc_t_unit_flops.restype = C.c_double
+    lib.mpqc_t_plan.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.POINTER(PlanInfo)]
+    lib.mpqc_t_plan.restype = C.c_int
     lib.mpqc_t_device_count.argtypes = []
     lib.mpqc_t_device_count.restype = C.c_int
     lib.mpqc_t_version.restype = C.c_char_p

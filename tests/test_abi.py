@@ -134,3 +134,24 @@ def test_plain_c_host_reproduces_reference_h2o(lib, tmp_path):
     e = float(res.stdout.split("E(T) =")[1].split()[0])
     assert abs(e - (-0.000868413807153793)) < 1e-11
     assert "(T) Energy:" in res.stdout
+
+
+def test_tiling_plan_of_the_baseline_configs(lib):
+    # host-only planning: the W-contraction tiling for BASELINE.json's shapes and its padding efficiency
+    def plan(o, v, flat):
+        info = L.PlanInfo()
+        assert lib.mpqc_t_plan(o, v, flat, C.byref(info)) == L.OK
+        return info
+    t = plan(63, 297, 1)                    # uracil trimer: flat rows, 3 column tiles of 13 fragments, last one short
+    assert (t.kp, t.row_tiles, t.col_tiles, t.nfrag, t.skip_last) == (360, 690, 3, 13, 1)
+    assert t.energy_tile_sets == 38 * 39 * 40 // 6
+    assert 0.975 < t.flop_efficiency < 0.98            # 297/304 columns, 88209/88320 rows
+    assert abs(t.bytes_operands - (2 * 63 * 297 * 297 * 360 + 63 * 63 * 297 * 360 + 63 * 63 * 297 * 297) * 8) < 1
+    p = plan(63, 297, 0)                    # patch mode of the same shape: odd row patch, ~4% more padding
+    assert p.tp * p.tq <= 128 and p.tp % 2 == 1 and 0.93 < p.flop_efficiency < t.flop_efficiency
+    for (o, v, lo) in [(21, 93, 0.90), (42, 198, 0.97), (40, 530, 0.94), (50, 500, 0.975), (4, 8, 0.2)]:
+        info = plan(o, v, 1)
+        assert info.nfrag * 8 * info.col_tiles - 8 * info.skip_last >= v
+        assert info.kp % 8 == 0 and info.kp >= v + o and info.flop_efficiency > lo, (o, v, info.flop_efficiency)
+    bad = L.PlanInfo()
+    assert lib.mpqc_t_plan(0, 5, 1, C.byref(bad)) == L.ERR_BAD_ARG
