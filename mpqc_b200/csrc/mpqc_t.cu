@@ -940,8 +940,7 @@ int energy_impl(const int64_t prob_o, const int64_t prob_v, const UploadFn& uplo
   int64_t count = (opt.unit_count < 0 || opt.unit_count > avail) ? avail : opt.unit_count;
   std::vector<int64_t> units((size_t)count);
   for (int64_t u = 0; u < count; ++u) units[u] = opt.unit_first + u * stride;
-  std::vector<double> unit_e((size_t)count, 0.0);
-  std::vector<int> owner((size_t)count, -1);   // which GPU produced each unit (for the NCCL sum)
+  std::vector<double> unit_e((size_t)count, 0.0);   // each slot is written by exactly one worker thread
   std::vector<int> all;
   build_triple_list(p->o, all);
 
@@ -1006,6 +1005,7 @@ int energy_impl(const int64_t prob_o, const int64_t prob_v, const UploadFn& uplo
     if (rc == MPQC_T_OK) rc = upload(h, &gs);
     const double tw2 = now_s();
     if (workers_uploaded.fetch_add(1) + 1 == ngpu) nccl_start();
+    std::vector<int64_t> done_idx;     // slots of unit_e this worker produced (for its NCCL contribution)
     if (rc == MPQC_T_OK) {
       // static part
       std::vector<int64_t> mine;
@@ -1017,7 +1017,7 @@ int energy_impl(const int64_t prob_o, const int64_t prob_v, const UploadFn& uplo
       if (rc == MPQC_T_OK)
         for (size_t q = 0; q < mine.size(); ++q) {
           unit_e[mine[q]] = e[q];
-          owner[mine[q]] = g;
+          done_idx.push_back(mine[q]);
         }
       // work-stealing tail
       int64_t chunk = opt.steal_chunk > 0 ? opt.steal_chunk : std::max<int64_t>(1, auto_batch(h)) * 4;
@@ -1030,7 +1030,7 @@ int energy_impl(const int64_t prob_o, const int64_t prob_v, const UploadFn& uplo
         if (rc == MPQC_T_OK)
           for (int64_t q = 0; q < n; ++q) {
             unit_e[s + q] = e2[q];
-            owner[s + q] = g;
+            done_idx.push_back(s + q);
           }
       }
     }
@@ -1048,11 +1048,8 @@ int energy_impl(const int64_t prob_o, const int64_t prob_v, const UploadFn& uplo
         r2 = fail(MPQC_T_ERR_OOM, "allocation for the NCCL sum failed", __FILE__, __LINE__);
       } else {
         std::vector<double> mine((size_t)count, 0.0);
-        if (rc == MPQC_T_OK) {
-          // this thread's contributions: unit_e holds every thread's results, so mask by ownership
-          for (int64_t u = 0; u < count; ++u)
-            if (owner[u] == g) mine[u] = unit_e[u];
-        }
+        if (rc == MPQC_T_OK)
+          for (int64_t u : done_idx) mine[u] = unit_e[u];   // only the slots this thread wrote itself
         cudaMemcpyAsync(dbuf, mine.data(), (size_t)count * sizeof(double), cudaMemcpyHostToDevice, st);
         int r = nc.AllReduce(dbuf, dbuf, (size_t)count, kNcclFloat64, kNcclSum, comms[g], st);
         if (r != 0) r2 = fail(MPQC_T_ERR_NCCL, nc.GetErrorString ? nc.GetErrorString(r) : "ncclAllReduce failed", __FILE__, __LINE__);
