@@ -98,8 +98,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+// Bounded wait: a barrier that never completes (a bad tensor map, a lost TMA transaction) must surface as an error
+// code at the C ABI, not as a hung GPU.  Legitimate waits last microseconds; after kMbarTimeoutNs of failed polls the
+// kernel traps, the launch fails with a CUDA error and the entry point returns MPQC_T_ERR_CUDA.
+constexpr unsigned long long kMbarTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  unsigned long long t0 = 0;
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if ((++polls & 0x3fffu) == 0) {
+      const unsigned long long t = global_timer_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > kMbarTimeoutNs) __trap();
+    }
   }
 }
 

@@ -63,9 +63,11 @@ def make_problem(o: int, v: int, seed: int = SEED, scale: float | None = None, n
 
 
 def make_problem_torch(o: int, v: int, device, seed: int = SEED, scale: float | None = None,
-                       naux: int | None = None):
+                       naux: int | None = None, dense_abci: bool = True):
     """Same construction on a CUDA device with torch (plumbing: used only to put synthetic
-    inputs into HBM for bench.py / large-size tests; not bit-identical to the numpy version)."""
+    inputs into HBM for bench.py / large-size tests; not bit-identical to the numpy version).
+    ``dense_abci=False`` skips the v^3 o tensor (density-fitted hand-off: only the three-centre factors
+    exist); every other array is identical to the dense call with the same seed."""
     import torch
     if scale is None:
         scale = calibrated_scale(o, v)
@@ -91,16 +93,18 @@ def make_problem_torch(o: int, v: int, device, seed: int = SEED, scale: float | 
     g_aijk = g_ikja.permute(3, 0, 2, 1).contiguous()
     del g_ikja
     # (ib|ac) -> [a,b,c,i]; build per a-slab to bound the transient
-    g_abci = torch.empty(v, v, v, o, device=device, dtype=f64)
-    lvv2 = l_vv.reshape(naux, v * v)
-    slab = max(1, min(v, (1 << 28) // max(1, v * v * o)))
-    for a0 in range(0, v, slab):
-        a1 = min(v, a0 + slab)
-        # (ac|ib): rows (a,c) for a in slab
-        blk = lvv2[:, a0 * v:a1 * v].t() @ lov2                 # [(a c), (i b)]
-        blk = blk.reshape(a1 - a0, v, o, v)                      # a c i b
-        g_abci[a0:a1] = blk.permute(0, 3, 1, 2)                  # a b c i
-        del blk
+    g_abci = None
+    if dense_abci:
+        g_abci = torch.empty(v, v, v, o, device=device, dtype=f64)
+        lvv2 = l_vv.reshape(naux, v * v)
+        slab = max(1, min(v, (1 << 28) // max(1, v * v * o)))
+        for a0 in range(0, v, slab):
+            a1 = min(v, a0 + slab)
+            # (ac|ib): rows (a,c) for a in slab
+            blk = lvv2[:, a0 * v:a1 * v].t() @ lov2                 # [(a c), (i b)]
+            blk = blk.reshape(a1 - a0, v, o, v)                      # a c i b
+            g_abci[a0:a1] = blk.permute(0, 3, 1, 2)                  # a b c i
+            del blk
     d2 = (eps_occ[None, None, :, None] + eps_occ[None, None, None, :]
           - eps_vir[:, None, None, None] - eps_vir[None, :, None, None])
     t2 = (g_abij / d2).contiguous()
