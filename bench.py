@@ -1,14 +1,19 @@
 #!/usr/bin/env python
-"""bench.py -- (T) throughput of the B200 path on the uracil-trimer/6-31G* shaped workload.
+"""bench.py -- (T) throughput of the B200 path on the uracil-trimer/6-31G* shaped workload, STRONG scaling.
 
     python bench.py --gpus N --steps K --warmup W            # our arm (N>1: launched by torchrun)
     python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port of the reference's
                                                              # default 'coarse' (T) on the box's host cores
 
-A "step" is one pass of the hot path over one batch of `--units` occupied triples (i>=j>=k) per GPU of the
-synthetic o=63, v=297 problem (BASELINE.json configs[3], the config the metric is quoted on; it fits one
-GPU).  metric = FP64 TFLOP/s with the algorithmic work model 12 v^3 (v+o) FLOPs per triple
-(= 2 o^3 v^3 (v+o) for the whole job).  Prints ONE JSON line on rank 0.
+A "step" is one pass of the hot path over ONE FIXED JOB: `--job-units` (4144) occupied triples i>=j>=k spread evenly
+over the unit list of the synthetic o=63, v=297 problem (BASELINE.json configs[3], the config the metric is quoted
+on; it fits one GPU).  With N GPUs the same job is sharded over the N ranks (job positions rank, rank+N, ...), inputs
+replicated, and the step ends with the path's one collective, an ncclAllReduce of the unit-energy vector inside the
+library (mpqc_t_run_comm) -- so "scaling" is "strong": total work per step does not grow with N.
+metric = FP64 TFLOP/s with the algorithmic work model 12 v^3 (v+o) FLOPs per triple (= 2 o^3 v^3 (v+o) for the whole
+(T)).  Prints ONE JSON line on rank 0; `parity` in it proves the N-GPU result equals the
+single-GPU one and the CPU oracle; `e2e` is the same job through mpqc_t_energy_comm on pinned HOST buffers;
+`in_process` (N > 1) runs the same job through the library's own one-process/N-threads path on rank 0.
 """
 from __future__ import annotations
 
@@ -42,13 +47,15 @@ FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 * 1e-12     # 148 SMs x 64 DFMA/clk
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="uracil-trimer-6-31Gs", choices=sorted(WORKLOADS))
-    ap.add_argument("--units", type=int, default=74, help="occupied triples per GPU per step")
-    ap.add_argument("--e2e-units", type=int, default=2048, help="triples per GPU in the end-to-end (host buffer) call")
+    ap.add_argument("--job-units", type=int, default=4144,
+                    help="occupied triples of the fixed job one step processes (sharded over the GPUs)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-in-process", action="store_true", help="skip the one-process/N-threads leg (N > 1, rank 0)")
+    ap.add_argument("--oracle-units", type=int, default=2, help="job units re-computed by the CPU oracle for `parity`")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-blocks", type=int, default=8, help="(a,b,c) virtual-block triples in the CPU sample")
     return ap.parse_args()
@@ -162,6 +169,32 @@ def as_numpy(hd: dict):
 
 
 # -------------------------------------------------------------------------------------------------
+def job_of(args, nt):
+    """The fixed job (the same for every N): JOB consecutive units from the middle of the i-major unit list -- a
+    contiguous slice of the real whole-(T) job, so the operand-panel locality of the timed work is the real job's."""
+    job = max(1, min(args.job_units, nt))
+    return job, max(0, (nt - job) // 2)
+
+
+def config_for(args, o, v, desc, job, first):
+    """Identical in both arms (ours / reference): names the workload, nothing else."""
+    return {"workload": f"{args.workload}: o={o}, v={v} ({desc})",
+            "job": f"{job} consecutive occupied triples i>=j>=k (units {first}..{first + job - 1} of the i-major list, "
+                   "the middle of the whole job); one unit = 12 v^3 (v+o) FLOPs",
+            "l2": "inputs larger than L2 (A operand panels %.1f GB; a step walks panels of every occupied index)"
+                  % (o * v * v * (v + o) * 8 / 1e9)}
+
+
+class DeviceSlices:
+    """numpy view of a device tensor for the CPU oracle: every [] pulls just that slice to the host."""
+
+    def __init__(self, t):
+        self.t, self.shape = t, tuple(t.shape)
+
+    def __getitem__(self, idx):
+        return self.t[idx].contiguous().cpu().numpy()
+
+
 def run_reference(args):
     """CPU arm: the reference's own algorithm for this path (oracle port; the reference binary cannot be built
     here) on the host cores.  Rank 0 only."""
@@ -179,6 +212,8 @@ def run_reference(args):
     else:
         from mpqc_b200.synthetic import make_problem
         host = make_problem(o, v)
+    nt = o * (o + 1) * (o + 2) // 6 - o
+    job, first = job_of(args, nt)
     cores = os.cpu_count()
     workers, blas_threads = cpu_workers()
     for _ in range(args.warmup):
@@ -193,14 +228,14 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "(T) FP64 TFLOP/s (algorithmic 2 o^3 v^3 (v+o) work model)", "value": value,
         "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": wall / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": wall / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: o={o}, v={v} ({desc})",
-                   "step": f"{workers} strictly ordered (a>b>c) virtual-block triples (block 8) of the reference's coarse "
-                           f"loop, run concurrently ({workers} workers x {blas_threads} BLAS threads)"},
+        "config": config_for(args, o, v, desc, job, first),
         "cpu_baseline": {"value": value, "unit": "TFLOP/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps x {workers} (a>b>c) block triples (vir block 8) of ccsd_t.h:443-640, "
-                                   f"numpy/OpenBLAS, {workers} concurrent block workers x {blas_threads} BLAS threads"},
+                         "sample": f"each step = {workers} strictly ordered (a>b>c) virtual-block triples (block 8) of the "
+                                   f"reference's coarse loop (ccsd_t.h:443-640) on the same inputs, a bounded sample of the "
+                                   f"job's work (rate is per FLOP of the same 2 o^3 v^3 (v+o) model); numpy/OpenBLAS, "
+                                   f"{workers} concurrent block workers x {blas_threads} BLAS threads; {args.steps} steps"},
         "e2e": {"value": value, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -220,16 +255,40 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the (T) path has no CPU fallback")
     torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    host_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        host_group = dist.new_group(backend="gloo")          # host-side barriers that keep the GPUs idle
     if args.gpus != world and rank == 0 and world > 1:
         print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
     n_gpus = world
 
+    def fmax(*xs):
+        t = torch.tensor(list(xs), dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.cpu()]
+
+    def fsum(*xs):
+        t = torch.tensor(list(xs), dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(x) for x in t.cpu()]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def host_barrier():
+        if world > 1:
+            dist.barrier(group=host_group)
+
     lib = L.load()
     o, v, desc = WORKLOADS[args.workload]
-    pd = make_problem_torch(o, v, f"cuda:{local}")          # same seed on every rank: replicated inputs
+    pd = make_problem_torch(o, v, dev)                       # same seed on every rank: replicated inputs
     torch.cuda.synchronize()
     prob = L.make_problem(o, v, pd["eps_occ"], pd["eps_vir"], pd["t1"], pd["t2"], pd["g_abij"], pd["g_aijk"], pd["g_abci"])
     h = C.c_void_p()
@@ -238,30 +297,34 @@ def run_ours(args):
     L.check(lib.mpqc_t_upload(h, C.byref(prob), 1, C.byref(up)), "mpqc_t_upload")
     nt = lib.mpqc_t_triple_count(o)
     unit_flops = lib.mpqc_t_unit_flops(o, v)
-    U = max(1, min(args.units, nt // max(1, n_gpus)))
-    stream = torch.cuda.ExternalStream(lib.mpqc_t_stream(h), device=f"cuda:{local}")
+    JOB, F = job_of(args, nt)
+
+    # ---- the (T) communicator of the library (rank mode): NCCL id from rank 0, broadcast by the host program ----
+    uid = L.UniqueId()
+    if rank == 0 and world > 1:
+        L.check(lib.mpqc_t_comm_unique_id(C.byref(uid)), "mpqc_t_comm_unique_id")
+    if world > 1:
+        t = torch.frombuffer(bytearray(bytes(uid)), dtype=torch.uint8).to(dev)
+        dist.broadcast(t, 0)
+        C.memmove(C.byref(uid), bytes(t.cpu().numpy().tobytes()), 128)
+    comm = C.c_void_p()
+    t0 = time.perf_counter()
+    L.check(lib.mpqc_t_comm_create_rank(C.byref(comm), world, rank, C.byref(uid), local), "mpqc_t_comm_create_rank")
+    comm_setup_s = time.perf_counter() - t0
+
+    stream = torch.cuda.ExternalStream(lib.mpqc_t_stream(h), device=dev)
     os.environ["MPQC_T_PROFILE"] = "1"                      # per-kernel CUDA-event split inside the library
+    unit_e = np.zeros(JOB)
+    e_job = C.c_double()
 
-    e_acc = torch.zeros(1, dtype=torch.float64, device=f"cuda:{local}")
-
-    def step(s, st):
-        first = ((s * n_gpus * U) + rank) % max(1, nt - n_gpus * U)
-        e = C.c_double()
-        L.check(lib.mpqc_t_run(h, first, n_gpus, U, 0, C.byref(e), None, C.byref(st)), "mpqc_t_run")
-        if world > 1:
-            t = torch.tensor([e.value], dtype=torch.float64, device=f"cuda:{local}")
-            dist.all_reduce(t)                               # the path's one collective (gop.sum, ccsd_t.h:692)
-            e_acc.add_(t)
-        return e.value
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def step(st):
+        # one pass over the fixed job: this rank's share + the library-side ncclAllReduce of the unit energies
+        L.check(lib.mpqc_t_run_comm(h, comm, F, 1, JOB, 0, C.byref(e_job), unit_e.ctypes.data_as(L.c_double_p),
+                                    C.byref(st)), "mpqc_t_run_comm")
 
     dummy = L.Stats()
-    for s in range(args.warmup):
-        step(s, dummy)
+    for _ in range(args.warmup):
+        step(dummy)
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -270,26 +333,25 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     ev0.record(stream)
-    for s in range(args.steps):
-        step(args.warmup + s, st)
+    for _ in range(args.steps):
+        step(st)
     ev1.record(stream)
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
-    dev_s = ev0.elapsed_time(ev1) * 1e-3
-    times = torch.tensor([dev_s, wall, st.seconds_contract, st.seconds_energy], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_s, wall, t_contract, t_energy = (float(x) for x in times.cpu())
-    total_units = args.steps * U * n_gpus
-    value = total_units * unit_flops / dev_s * 1e-12
+    dev_s, wall, t_contract, t_energy, t_compute = fmax(ev0.elapsed_time(ev1) * 1e-3, wall, st.seconds_contract,
+                                                        st.seconds_energy, st.seconds_compute)
+    launches_all, flops_all = fsum(float(st.kernel_launches), st.flops)
+    value = args.steps * JOB * unit_flops / dev_s * 1e-12
+    e_job_dev = e_job.value
+    unit_e_dev = unit_e.copy()
 
-    # ---- roofline of the dominant kernel (W contraction, FP64 tensor pipe) -----------------------------------
+    # ---- roofline of the dominant kernel (W contraction, FP64 tensor pipe), this rank's launches ---------------
     tf_peak = C.c_double()
     L.check(lib.mpqc_t_microbench(local, 0, C.byref(tf_peak)), "microbench")
-    n_gemm_launches = st.kernel_launches // 3
-    per_launch_flops = st.flops / max(1, n_gemm_launches)
-    achieved = st.flops / max(t_contract, 1e-12) * 1e-12
+    n_gemm_launches = max(1, (st.kernel_launches - args.steps * (1 if world > 1 else 0)) // 3)
+    per_launch_flops = st.flops / n_gemm_launches
+    achieved = st.flops / max(st.seconds_contract, 1e-12) * 1e-12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
@@ -301,82 +363,115 @@ def run_ours(args):
                 "unit": "TFLOP/s", "frac": achieved / tf_peak.value, "traffic": traffic,
                 "peak_source": "FP64 tensor peak is not in MEASURED_PEAKS.json; measured live with the DMMA.8x8x4 "
                                "issue-rate microbenchmark (mpqc_t_microbench); nominal 148 SM x 64 FMA/clk x 1.965 GHz "
-                               f"= {FP64_NOMINAL_TFLOPS:.1f}",
-                "flops_per_launch": per_launch_flops, "launch_ms": t_contract / max(1, n_gemm_launches) * 1e3,
-                "share_of_step": t_contract / max(1e-12, st.seconds_compute)}
-    hbm_peak = None
+                               f"= {FP64_NOMINAL_TFLOPS:.1f}; ncu sm__ops_path_tensor_src_fp64 peak_sustained agrees (profiles/)",
+                "flops_per_launch": per_launch_flops, "launch_ms": st.seconds_contract / n_gemm_launches * 1e3,
+                "share_of_step": st.seconds_contract / max(1e-12, st.seconds_compute)}
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
         hbm_src = "MEASURED_PEAKS.json"
     except Exception:
         hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
     e_bytes = st.units * 3.0 * 8.0 * v ** 3
-    roofline_energy = {"kernel": "t_energy_fused_kernel", "bound": "hbm", "achieved": e_bytes / max(t_energy, 1e-12) * 1e-9,
-                       "peak": hbm_peak, "unit": "GB/s", "frac": e_bytes / max(t_energy, 1e-12) * 1e-9 / hbm_peak,
-                       "peak_source": hbm_src, "share_of_step": t_energy / max(1e-12, st.seconds_compute)}
+    roofline_energy = {"kernel": "t_energy_fused_kernel", "bound": "hbm",
+                       "achieved": e_bytes / max(st.seconds_energy, 1e-12) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                       "frac": e_bytes / max(st.seconds_energy, 1e-12) * 1e-9 / hbm_peak, "peak_source": hbm_src,
+                       "bytes_model": "3 x 8 v^3 per triple (the three pair-GEMM outputs are read once)",
+                       "share_of_step": st.seconds_energy / max(1e-12, st.seconds_compute)}
+
+    # ---- parity: the N-GPU job result vs the single-GPU path and vs the CPU oracle ------------------------------
+    parity = {"job_energy": e_job_dev, "units": JOB}
+    if rank == 0:
+        # (a) the same job on ONE GPU through mpqc_t_run (N = 1 path, no communicator): must agree bit for bit
+        n_single = JOB if world > 1 else min(JOB, 296)       # at N = 1 re-run a slice with another batch size
+        ue1 = np.zeros(n_single)
+        e1 = C.c_double()
+        L.check(lib.mpqc_t_run(h, F, 1, n_single, 0 if world > 1 else 3, C.byref(e1), ue1.ctypes.data_as(L.c_double_p), None),
+                "mpqc_t_run")
+        parity["single_gpu_units_recomputed"] = int(n_single)
+        parity["unit_max_abs_diff"] = float(np.max(np.abs(ue1 - unit_e_dev[:n_single])))
+        parity["abs_diff"] = abs(float(np.sum(ue1)) - float(np.sum(unit_e_dev[:n_single])))
+        # (b) CPU oracle (energy_ijk, ccsd_t.h:1142-1167 at fixed i,j,k) on a few job units, read through lazy slices
+        from oracle import ccsd_t_oracle as oc
+        oargs = (pd["t1"].cpu().numpy(), DeviceSlices(pd["t2"]), DeviceSlices(pd["g_abij"]), DeviceSlices(pd["g_aijk"]),
+                 DeviceSlices(pd["g_abci"]), pd["eps_occ"].cpu().numpy(), pd["eps_vir"].cpu().numpy())
+        worst, i32 = 0.0, [C.c_int32() for _ in range(3)]
+        picks = [int(q) for q in np.linspace(0, JOB - 1, max(1, args.oracle_units)).astype(int)] if args.oracle_units > 0 else []
+        for q in picks:
+            L.check(lib.mpqc_t_triple_of_unit(o, F + q, *[C.byref(x) for x in i32]), "triple_of_unit")
+            i, j, k = (x.value for x in i32)
+            worst = max(worst, abs(oc.triple_weight(i, j, k) * oc.energy_ijk(*oargs, i, j, k) - unit_e_dev[q]))
+        parity["oracle_units_checked"] = len(picks)
+        parity["oracle_max_abs_diff"] = worst
+        parity["tolerance"] = 1e-10
 
     # ---- end to end through the reference-facing call with HOST buffers ---------------------------------------
-    e2e = None
-    e2e_df = None
+    e2e = e2e_df = in_process = None
     host = None
+    lib.mpqc_t_destroy(h)                                   # free the resident copy: the e2e calls own their memory
+    h = None
     if not args.no_e2e:
         host = to_host(pd, pin=True)
-        hp = L.make_problem(o, v, host["eps_occ"], host["eps_vir"], host["t1"], host["t2"], host["g_abij"],
-                            host["g_aijk"], host["g_abci"])
-        EU = max(1, min(args.e2e_units, nt // n_gpus))
-        opt = L.Options()
-        opt.ngpu = 1
-        dev_ids = (C.c_int32 * 1)(local)
-        opt.device_ids = dev_ids
-        opt.unit_first, opt.unit_stride, opt.unit_count = rank, n_gpus, EU
-        lib.mpqc_t_destroy(h)                               # free the resident copy: the e2e call owns its memory
-        h = None
         del pd
         torch.cuda.empty_cache()
+        hp = L.make_problem(o, v, host["eps_occ"], host["eps_vir"], host["t1"], host["t2"], host["g_abij"],
+                            host["g_aijk"], host["g_abci"])
+        opt = L.Options()
+        opt.unit_first, opt.unit_stride, opt.unit_count = F, 1, JOB
         # two identical calls: the first is the warm-up of this path (first large cudaMalloc after torch released its
         # pool, first touch of the pinned pages), the second is the one reported; both durations are in the JSON
         ewalls = []
         for _rep in range(2):
             barrier()
-            est = L.Stats()
-            e = C.c_double()
+            est, e = L.Stats(), C.c_double()
             t0 = time.perf_counter()
-            L.check(lib.mpqc_t_energy(C.byref(hp), C.byref(opt), C.byref(e), C.byref(est)), "mpqc_t_energy")
-            if world > 1:
-                t = torch.tensor([e.value], dtype=torch.float64, device=f"cuda:{local}")
-                dist.all_reduce(t)
-            torch.cuda.synchronize()
-            ewall = time.perf_counter() - t0
-            tt = torch.tensor([ewall], dtype=torch.float64, device=f"cuda:{local}")
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ewalls.append(float(tt.cpu()[0]))
+            L.check(lib.mpqc_t_energy_comm(comm, C.byref(hp), C.byref(opt), C.byref(e), C.byref(est)), "mpqc_t_energy_comm")
+            ewalls.append(fmax(time.perf_counter() - t0)[0])
         ewall = ewalls[-1]
-        esteps = EU / U
-        # same call with the density-fitting factors in place of the dense integrals: the
-        # v^3 o tensor is assembled on the device, so ~6x fewer bytes cross PCIe
+        h2d_all, d2h_all = fsum(float(est.bytes_h2d), float(est.bytes_d2h))
+        up_s, rel_s, comp_s = fmax(est.seconds_upload, est.seconds_relayout, est.seconds_compute)
+        e2e = {"value": JOB * unit_flops / ewall * 1e-12, "unit": "TFLOP/s",
+               "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
+               "seconds": ewall, "seconds_warmup_call": ewalls[0], "seconds_upload": up_s,
+               "seconds_relayout": rel_s, "seconds_compute": comp_s, "abs_diff_vs_device_job": abs(e.value - e_job_dev),
+               "call": "mpqc_t_energy_comm(pinned host buffers): every rank uploads 1/N of each input over its own PCIe "
+                       "link + ncclAllGather over NVLink, relayout, this rank's share of the job, ncclAllReduce of the "
+                       "unit energies, D2H; bytes are summed over the ranks"}
+        # same call with the density-fitting factors in place of the dense integrals
         dfp = L.make_df_problem(o, v, int(host["naux"]), host["eps_occ"], host["eps_vir"], host["t1"], host["t2"],
                                 host["x_ab"], host["x_ij"], host["x_ai"])
-        dst, de = L.Stats(), C.c_double()
         barrier()
+        dst, de = L.Stats(), C.c_double()
         t0 = time.perf_counter()
-        L.check(lib.mpqc_t_energy_df(C.byref(dfp), C.byref(opt), C.byref(de), C.byref(dst)), "mpqc_t_energy_df")
-        torch.cuda.synchronize()
-        dwall = time.perf_counter() - t0
-        tt = torch.tensor([dwall], dtype=torch.float64, device=f"cuda:{local}")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dwall = float(tt.cpu()[0])
-        e2e_df = {"value": EU * n_gpus * unit_flops / dwall * 1e-12, "unit": "TFLOP/s",
-                  "h2d_bytes_per_step": dst.bytes_h2d / esteps, "seconds": dwall, "seconds_upload": dst.seconds_upload,
-                  "seconds_relayout": dst.seconds_relayout, "abs_diff_vs_dense_call": abs(de.value - e.value),
-                  "call": "mpqc_t_energy_df(host buffers): t2 + three-centre factors cross PCIe, integrals assembled on device"}
-        e2e = {"value": EU * n_gpus * unit_flops / ewall * 1e-12, "unit": "TFLOP/s",
-               "h2d_bytes_per_step": est.bytes_h2d / esteps, "d2h_bytes_per_step": est.bytes_d2h / esteps,
-               "units_per_gpu": EU, "seconds": ewall, "seconds_warmup_call": ewalls[0],
-               "seconds_upload": est.seconds_upload,
-               "seconds_relayout": est.seconds_relayout, "seconds_compute": est.seconds_compute,
-               "call": "mpqc_t_energy(host buffers) = H2D of all inputs + relayout + triples + D2H of unit energies"}
+        L.check(lib.mpqc_t_energy_df_comm(comm, C.byref(dfp), C.byref(opt), C.byref(de), C.byref(dst)), "mpqc_t_energy_df_comm")
+        dwall = fmax(time.perf_counter() - t0)[0]
+        e2e_df = {"value": JOB * unit_flops / dwall * 1e-12, "unit": "TFLOP/s",
+                  "h2d_bytes_per_step": fsum(float(dst.bytes_h2d))[0], "seconds": dwall,
+                  "seconds_upload": fmax(dst.seconds_upload)[0], "seconds_relayout": fmax(dst.seconds_relayout)[0],
+                  "abs_diff_vs_dense_call": abs(de.value - e.value),
+                  "call": "mpqc_t_energy_df_comm(host buffers): t2 + three-centre factors cross PCIe, integrals assembled on device"}
+
+        # ---- the library's own one-process / N-threads path on all N GPUs (rank 0; the other ranks idle) -------
+        if world > 1 and not args.no_in_process:
+            host_barrier()                                  # everyone's device memory is free again
+            if rank == 0:
+                lc = C.c_void_p()
+                t0 = time.perf_counter()
+                L.check(lib.mpqc_t_comm_create_local(C.byref(lc), world, None), "mpqc_t_comm_create_local")
+                setup_s = time.perf_counter() - t0
+                walls = []
+                for _rep in range(2):
+                    ist, ie = L.Stats(), C.c_double()
+                    t0 = time.perf_counter()
+                    L.check(lib.mpqc_t_energy_comm(lc, C.byref(hp), C.byref(opt), C.byref(ie), C.byref(ist)), "mpqc_t_energy_comm(local)")
+                    walls.append(time.perf_counter() - t0)
+                lib.mpqc_t_comm_destroy(lc)
+                in_process = {"n_gpus": world, "value": JOB * unit_flops / walls[-1] * 1e-12, "unit": "TFLOP/s",
+                              "seconds": walls[-1], "seconds_warmup_call": walls[0], "seconds_comm_setup": setup_s,
+                              "seconds_upload": ist.seconds_upload, "seconds_compute": ist.seconds_compute,
+                              "abs_diff_vs_device_job": abs(ie.value - e_job_dev),
+                              "call": "mpqc_t_comm_create_local + mpqc_t_energy_comm in ONE process: one host thread per GPU, "
+                                      "static share + work-stealing tail, NVLink input replication, ncclAllReduce sum"}
+            host_barrier()
 
     # ---- CPU baseline on rank 0 at N=1 ---------------------------------------------------------------------------
     cpu = None
@@ -390,23 +485,22 @@ def run_ours(args):
                          f"{cpu_workers()[0]} concurrent block workers x {cpu_workers()[1]} BLAS threads, {dt:.1f} s"}
 
     if rank == 0:
+        cfg = config_for(args, o, v, desc, JOB, F)
         line = {
             "metric": "(T) FP64 TFLOP/s (algorithmic 2 o^3 v^3 (v+o) work model)", "value": value, "unit": "TFLOP/s",
             "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: o={o}, v={v} ({desc})", "units_per_gpu_per_step": U,
-                       "unit": "one occupied triple i>=j>=k = 12 v^3 (v+o) FLOPs", "parallelism": f"triple-sharded x{n_gpus}",
-                       "l2": "inputs larger than L2 (A operand panels %.1f GB; every step walks different triples)"
-                             % (o * v * v * (v + o) * 8 / 1e9),
-                       "projected_full_job_s": lib.mpqc_t_triple_count(o) * unit_flops / (value * 1e12)},
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": cfg,
+            "parallelism": f"job sharded over {n_gpus} rank(s), one per GPU; inputs replicated; one ncclAllReduce per step",
+            "projected_full_job_s": nt * unit_flops / (value * 1e12),
             "pct_fp64_tensor_peak": 100.0 * value / n_gpus / tf_peak.value,
-            "wall_ms_per_step": wall / args.steps * 1e3,
-            "roofline": roofline, "roofline_energy": roofline_energy, "cpu_baseline": cpu, "e2e": e2e, "e2e_df": e2e_df,
-            "gpu_launches": int(st.kernel_launches), "clocks": clocks,
+            "wall_ms_per_step": wall / args.steps * 1e3, "seconds_comm_setup": comm_setup_s,
+            "roofline": roofline, "roofline_energy": roofline_energy, "parity": parity, "cpu_baseline": cpu,
+            "e2e": e2e, "e2e_df": e2e_df, "in_process": in_process,
+            "gpu_launches": int(launches_all), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
-    if h is not None:
-        lib.mpqc_t_destroy(h)
+    lib.mpqc_t_comm_destroy(comm)
     if world > 1:
         dist.destroy_process_group()
 

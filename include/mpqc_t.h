@@ -32,13 +32,14 @@
 #ifndef MPQC_T_H
 #define MPQC_T_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define MPQC_T_ABI_VERSION 1
+#define MPQC_T_ABI_VERSION 2
 
 /* status codes (mapped to mpqc::Exception subclasses by the adapter, util/core/exception.h:93-593) */
 enum {
@@ -92,7 +93,8 @@ typedef struct mpqc_t_options {
   int64_t unit_count;         /* number of units to process; <0 -> all remaining with that stride */
   int32_t batch;              /* triples per kernel launch; 0 -> auto */
   int32_t steal_chunk;        /* in-process multi-GPU: triples per work-stealing grab; 0 -> auto */
-  int32_t use_nccl;           /* in-process multi-GPU: sum partial E(T) with ncclAllReduce (1) or on the host (0) */
+  int32_t use_nccl;           /* mpqc_t_energy with ngpu > 1 and no communicator: 1 = build a communicator for this call
+                                 (NVLink input replication + ncclAllReduce sum), 0 = replicated uploads + host sum */
   int32_t reserved[5];
 } mpqc_t_options;
 
@@ -114,6 +116,8 @@ typedef struct mpqc_t_stats {
 } mpqc_t_stats;
 
 typedef struct mpqc_t_handle mpqc_t_handle; /* opaque: one device's resident, re-laid-out problem */
+typedef struct mpqc_t_comm mpqc_t_comm;     /* opaque: the GPUs that share one (T) job, and their NCCL communicator */
+typedef struct mpqc_t_unique_id { char internal[128]; } mpqc_t_unique_id;   /* == ncclUniqueId */
 
 /* ---- one-shot entry point: what the adapter's compute_ccsd_t() calls ------------------------ */
 /* Computes this process' partial E(T) over its units (all units when unit_first=0, unit_stride=1,
@@ -123,7 +127,39 @@ int mpqc_t_energy(const mpqc_t_problem* p, const mpqc_t_options* opt, double* e_
 /* same contract, density-fitted inputs */
 int mpqc_t_energy_df(const mpqc_t_df_problem* p, const mpqc_t_options* opt, double* e_t, mpqc_t_stats* stats);
 
-/* ---- split-phase API (lets uploads be timed separately; used by bench.py and the tests) ------ */
+/* ---- multi-GPU form: a persistent communicator + one collective call ------------------------------------
+ * Replaces, inside the library, the reference's replicated integrals and its final  gop.sum  (ccsd_t.h:692):
+ *   - every rank calls mpqc_t_energy_comm with the SAME host problem and options; the job (unit_first, unit_stride,
+ *     unit_count of the options: all units by default) is sharded over the ranks of the communicator
+ *     (opt.ngpu / device_ids are ignored: the communicator names the devices);
+ *   - each host tensor crosses PCIe once in total: rank r copies 1/N of it over its own link and one ncclAllGather
+ *     over NVLink completes it on every GPU;
+ *   - the per-unit energies are summed by one ncclAllReduce and *e_t is the TOTAL E(T) of the job on every rank,
+ *     bit-identical to the single-GPU result.
+ * Two launch modes:
+ *   rank mode  - one MPI rank per GPU: rank 0 calls mpqc_t_comm_unique_id, the host program broadcasts the 128
+ *                bytes (world.gop.broadcast), every rank calls mpqc_t_comm_create_rank;
+ *   local mode - one process drives ngpu devices (one host thread per GPU inside the call, joined before it
+ *                returns; static share + work-stealing tail): mpqc_t_comm_create_local.
+ * Creating a communicator creates the CUDA contexts (in parallel) and the NCCL communicator, which takes seconds:
+ * do it once, e.g. when the wave function object is constructed, not per (T) call.  Errors are agreed upon
+ * collectively: if any rank fails (e.g. out of device memory) every rank returns an error instead of blocking. */
+int mpqc_t_comm_unique_id(mpqc_t_unique_id* id);
+int mpqc_t_comm_create_rank(mpqc_t_comm** c, int32_t nranks, int32_t rank, const mpqc_t_unique_id* id, int32_t device);
+int mpqc_t_comm_create_local(mpqc_t_comm** c, int32_t ngpu, const int32_t* device_ids /* NULL -> 0..ngpu-1 */);
+int mpqc_t_comm_size(const mpqc_t_comm* c);
+int mpqc_t_comm_destroy(mpqc_t_comm* c);
+int mpqc_t_energy_comm(mpqc_t_comm* c, const mpqc_t_problem* p, const mpqc_t_options* opt, double* e_t, mpqc_t_stats* stats);
+int mpqc_t_energy_df_comm(mpqc_t_comm* c, const mpqc_t_df_problem* p, const mpqc_t_options* opt, double* e_t,
+                          mpqc_t_stats* stats);
+
+/* page-locked host memory for the dense buffers the adapter gathers into (full PCIe speed for the uploads) */
+int mpqc_t_host_alloc(void** ptr, size_t bytes);
+int mpqc_t_host_free(void* ptr);
+
+/* ---- split-phase API (lets uploads be timed separately; used by bench.py and the tests) ------
+ * Device-resident inputs (on_device = 1) may have been produced on any stream of the caller: upload starts with a
+ * cudaDeviceSynchronize(), so no event hand-off is needed; the handle then works on its own non-blocking stream. */
 int mpqc_t_create(mpqc_t_handle** h, int64_t o, int64_t v, int32_t device);
 /* host (on_device=0) or device (on_device=1) buffers -> occupied-major operand layouts in HBM */
 int mpqc_t_upload(mpqc_t_handle* h, const mpqc_t_problem* p, int32_t on_device, mpqc_t_stats* stats);
@@ -134,6 +170,20 @@ int mpqc_t_upload_df(mpqc_t_handle* h, const mpqc_t_df_problem* p, int32_t on_de
  * unit_e (optional, may be NULL) receives the weighted per-unit energies [count].  batch 0 = auto. */
 int mpqc_t_run(mpqc_t_handle* h, int64_t first, int64_t stride, int64_t count, int32_t batch,
                double* partial_e, double* unit_e, mpqc_t_stats* stats);
+/* collective form of mpqc_t_run for one rank per GPU: (first, stride, count) name the JOB, every rank of the
+ * rank-mode communicator runs job positions rank, rank+R, ... on its own resident handle, and one ncclAllReduce on the
+ * handle's stream (device buffers; no host round trip before the collective) completes the job-length unit-energy
+ * vector on every rank.  total_e = E(T) of the whole job, identical on all ranks and for any R; unit_e (optional)
+ * receives the [count] unit energies of the job. */
+int mpqc_t_run_comm(mpqc_t_handle* h, mpqc_t_comm* c, int64_t first, int64_t stride, int64_t count, int32_t batch,
+                    double* total_e, double* unit_e, mpqc_t_stats* stats);
+/* same as mpqc_t_run, and additionally the decomposition of the SAME energy over virtual-block triples:
+ * vblock_e[tt], tt = 0 .. energy_tile_sets-1 (mpqc_t_plan), enumerates 8-wide virtual tiles TA >= TB >= TC in the
+ * order of the reference's coarse loop with block size 8 (global_iter - 1, ccsd_t.h:443-480).  Run over ALL units,
+ * vblock_e[tt] is the energy that loop iteration contributes (ccsd_t.h:619-638) and sum_tt vblock_e[tt] = E(T):
+ * the whole-job result can be checked against sampled iterations of the reference algorithm. */
+int mpqc_t_run_vblocks(mpqc_t_handle* h, int64_t first, int64_t stride, int64_t count, int32_t batch,
+                       double* partial_e, double* unit_e, double* vblock_e, mpqc_t_stats* stats);
 /* debugging / parity aid: W^{abc}_{ijk} of one occupied triple as a dense [v][v][v] host array */
 int mpqc_t_debug_w(mpqc_t_handle* h, int32_t i, int32_t j, int32_t k, double* w_host);
 /* CUDA stream the handle launches on (cudaStream_t as void*), for event timing by the caller */

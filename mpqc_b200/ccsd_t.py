@@ -192,11 +192,17 @@ class CCSD_T:
     ``FeatureDisabled``.
 
     Extra keywords of the GPU path: ``ngpu`` (devices driven by this process), ``device_ids``,
-    ``batch``, ``use_nccl`` (sum the per-GPU partials with ncclAllReduce), and -- one-rank-per-GPU mode -- ``rank`` / ``world_size`` (unit sharding; the caller sums
-    the partial energies with its own collective, replacing ``gop.sum`` at ccsd_t.h:692).
+    ``batch``, ``use_nccl`` (one-shot NCCL communicator for ``ngpu`` > 1).  Multi-rank use, one rank per GPU
+    (replaces ``gop.sum`` at ccsd_t.h:692), either
+      * ``comm=``: a library communicator (``mpqc_t_comm_create_rank`` / ``_local``, a ``ctypes.c_void_p``); the call
+        becomes ``mpqc_t_energy_comm``: inputs replicated over NVLink, unit energies summed by ncclAllReduce inside
+        the library, every rank gets the TOTAL E(T); or
+      * ``rank`` / ``world_size`` keywords + ``reduce=``: the unit list is sharded by stride and ``reduce(partial)``
+        (the host program's own sum, e.g. an MPI/torch all-reduce) must return the total.  A sharded run without
+        either raises ``InputError`` -- a partial E(T) is never stored as the energy.
     """
 
-    def __init__(self, kv: dict, ccsd=None, out=None):
+    def __init__(self, kv: dict, ccsd=None, out=None, comm=None, reduce=None):
         kv = dict(kv or {})
         t = kv.get("type", "CCSD(T)")
         if t != "CCSD(T)":
@@ -231,6 +237,11 @@ class CCSD_T:
             raise InputError("ngpu must be >= 1", "ngpu", self.ngpu_)
         if not (0 <= self.rank_ < self.world_size_):
             raise InputError("rank must satisfy 0 <= rank < world_size", "rank", self.rank_)
+        self._comm = comm
+        self._reduce = reduce
+        if self._comm is not None and self.world_size_ != 1:
+            raise InputError("give either a library communicator (comm=) or rank/world_size + reduce=, not both", "rank",
+                             self.rank_)
         self.triples_energy_ = 0.0
         self.computed_ = False
         self.stats_ = None
@@ -270,6 +281,9 @@ class CCSD_T:
         if self.approach_ == "laplace":
             raise FeatureDisabled("approach=laplace is a different (approximate) method; "
                                   "not provided by the GPU (T) path")
+        if self.world_size_ > 1 and self._reduce is None:
+            raise InputError("rank/world_size sharding needs reduce= (or use a library communicator, comm=): the partial "
+                             "E(T) of one rank must not be stored as the energy", "world_size", self.world_size_)
         t0 = time.perf_counter()
         print("\nBegining CCSD(T) ", file=self._out)
         cc = self._ccsd
@@ -280,6 +294,9 @@ class CCSD_T:
         eps_occ = eps[n_frozen:n_occ]                # ccsd_t.h:2306-2311: eps[i + n_frozen]
         eps_vir = eps[n_occ:n_occ + v]               # eps[a + n_occ]
         on_device = not isinstance(eps, np.ndarray) and getattr(eps, "is_cuda", False)
+        if on_device:
+            import torch
+            torch.cuda.current_stream().synchronize()    # producers of the device tensors (the library syncs the device too)
         if isinstance(eps, np.ndarray):
             eps_occ = np.ascontiguousarray(eps_occ, dtype=np.float64)
             eps_vir = np.ascontiguousarray(eps_vir, dtype=np.float64)
@@ -310,12 +327,17 @@ class CCSD_T:
         st = L.Stats()
         e = C.c_double(0.0)
         lib = L.load()
-        if use_df:
+        if self._comm is not None:
+            opt.unit_first, opt.unit_stride = 0, 1             # the communicator shards the whole unit list
+            fn = lib.mpqc_t_energy_df_comm if use_df else lib.mpqc_t_energy_comm
+            status = fn(self._comm, C.byref(prob), C.byref(opt), C.byref(e), C.byref(st))
+        elif use_df:
             status = lib.mpqc_t_energy_df(C.byref(prob), C.byref(opt), C.byref(e), C.byref(st))
         else:
             status = lib.mpqc_t_energy(C.byref(prob), C.byref(opt), C.byref(e), C.byref(st))
         _raise_for(status, "mpqc_t_energy_df" if use_df else "mpqc_t_energy")
-        self.triples_energy_ = e.value
+        # the partial of a stride-sharded run goes through the host program's sum before it becomes the energy
+        self.triples_energy_ = float(self._reduce(e.value)) if self.world_size_ > 1 else e.value
         self.stats_ = st.as_dict()
         print(f"(T) Energy: {self.triples_energy_} Time: {time.perf_counter() - t0} S ", file=self._out)
         return self.triples_energy_

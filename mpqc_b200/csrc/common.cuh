@@ -98,9 +98,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
-// Bounded wait: a barrier that never completes (a bad tensor map, a lost TMA transaction) must surface as an error
-// code at the C ABI, not as a hung GPU.  Legitimate waits last microseconds; after kMbarTimeoutNs of failed polls the
-// kernel traps, the launch fails with a CUDA error and the entry point returns MPQC_T_ERR_CUDA.
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity);
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef MPQC_T_BOUNDED_CONSUMER_WAIT   // A/B build only (scripts/ab_variants.sh): bounded wait in the consumers too
+  mbar_wait_bounded(bar, parity);
+#else
+  while (!mbar_try_wait(bar, parity)) {
+  }
+#endif
+}
+
+// Bounded wait, used by the TMA producer lane only (the DMMA consumers keep the tight loop above, so their hot path is
+// untouched).  A barrier that never completes (a bad tensor map,
+// a lost TMA transaction) must surface as an error code at the C ABI, not as a hung GPU: the producer outlives every
+// consumer wait (it drains the ring before it exits, w_contract.cuh), so if the pipeline stalls anywhere the producer
+// is the thread that notices -- after kMbarTimeoutNs of failed polls it traps, the launch fails with a CUDA error and
+// the entry point returns MPQC_T_ERR_CUDA.  Legitimate waits last microseconds.
 constexpr unsigned long long kMbarTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
 
 __device__ __forceinline__ unsigned long long global_timer_ns() {
@@ -109,7 +123,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   return t;
 }
 
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   unsigned long long t0 = 0;
   uint32_t polls = 0;

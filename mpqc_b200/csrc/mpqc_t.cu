@@ -21,6 +21,7 @@
 #include <functional>
 
 #include "common.cuh"
+#include "comm.cuh"
 #include "microbench.cuh"
 #include "relayout.cuh"
 #include "t_energy.cuh"
@@ -81,37 +82,22 @@ int encode_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, con
 
 int64_t roundup(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
-// ---- NCCL, bound at run time (dlopen) so the library has no link-time dependency and shares the NCCL that a
-//      host process (e.g. torch) may already have loaded.  Only the entry points the path needs: the final sum
-//      of the partial E(T) over NVLink (replaces gop.sum, ccsd_t.h:692). ----
-struct NcclApi {
-  typedef struct ncclComm* comm_t;
-  int (*CommInitAll)(comm_t*, int, const int*) = nullptr;
-  int (*CommDestroy)(comm_t) = nullptr;
-  int (*AllReduce)(const void*, void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
-  const char* (*GetErrorString)(int) = nullptr;
-  bool ok = false;
+// CUDA events released on every exit path
+struct EventList {
+  std::vector<cudaEvent_t> ev;
+  int add(cudaEvent_t* out) {
+    cudaEvent_t e;
+    MPQC_T_CUDA(cudaEventCreate(&e));
+    ev.push_back(e);
+    *out = e;
+    return MPQC_T_OK;
+  }
+  ~EventList() {
+    for (auto e : ev) cudaEventDestroy(e);
+  }
 };
 
-const NcclApi& nccl_api() {
-  static NcclApi api;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    const char* names[] = {"libnccl.so.2", "libnccl.so"};
-    void* hnd = nullptr;
-    for (const char* n : names) {
-      hnd = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
-      if (hnd) break;
-    }
-    if (!hnd) return;
-    api.CommInitAll = reinterpret_cast<decltype(api.CommInitAll)>(dlsym(hnd, "ncclCommInitAll"));
-    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(hnd, "ncclCommDestroy"));
-    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(hnd, "ncclAllReduce"));
-    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(hnd, "ncclGetErrorString"));
-    api.ok = api.CommInitAll && api.CommDestroy && api.AllReduce;
-  });
-  return api;
-}
+
 // ---- cuBLAS, bound at run time for the same reasons (plain library DGEMMs of the density-fitted upload only) ----
 struct BlasApi {
   cublasStatus_t (*Create)(cublasHandle_t*) = nullptr;
@@ -143,9 +129,6 @@ const BlasApi& blas_api() {
   });
   return api;
 }
-
-constexpr int kNcclFloat64 = 8;   // ncclDouble
-constexpr int kNcclSum = 0;
 
 }  // namespace
 
@@ -277,17 +260,30 @@ int auto_batch(const mpqc_t_handle* h) {
   return (int)std::min(nb, cap);
 }
 
-void build_triple_list(int64_t o, std::vector<int>& out) {
-  out.clear();
-  for (int i = 0; i < o; ++i)
-    for (int j = 0; j <= i; ++j)
-      for (int k = 0; k <= j; ++k) {
-        if (i == j && j == k) continue;
-        out.push_back(i);
-        out.push_back(j);
-        out.push_back(k);
-      }
-}
+// Unit enumeration (include/mpqc_t.h): i-major list of i >= j >= k without i == j == k.  Units are decoded by
+// arithmetic -- nothing of size O(o^3) is ever materialised on the host.
+struct UnitIndex {
+  std::vector<int64_t> start;   // start[i] = first unit whose leading index is i; start[o] = number of units
+  explicit UnitIndex(int64_t o) : start((size_t)o + 1) {
+    int64_t u = 0;
+    for (int64_t i = 0; i < o; ++i) {
+      start[(size_t)i] = u;
+      u += (i + 1) * (i + 2) / 2 - 1;   // (j,k) pairs with k <= j <= i, minus (i,i,i)
+    }
+    start[(size_t)o] = u;
+  }
+  int64_t count() const { return start.back(); }
+  void triple(int64_t unit, int& i, int& j, int& k) const {
+    const int64_t ii = (std::upper_bound(start.begin(), start.end(), unit) - start.begin()) - 1;
+    const int64_t r = unit - start[(size_t)ii];          // position inside the i group: j(j+1)/2 + k
+    int64_t jj = (int64_t)((std::sqrt(8.0 * (double)r + 1.0) - 1.0) * 0.5);
+    while (jj * (jj + 1) / 2 > r) --jj;
+    while ((jj + 1) * (jj + 2) / 2 <= r) ++jj;
+    i = (int)ii;
+    j = (int)jj;
+    k = (int)(r - jj * (jj + 1) / 2);
+  }
+};
 
 GemmParams gemm_params(const mpqc_t_handle* h, int nbatch, const int* triples_dev) {
   GemmParams P;
@@ -347,46 +343,80 @@ int launch_energy(mpqc_t_handle* h, int nbatch, const int* triples_dev, double* 
   return MPQC_T_OK;
 }
 
-// CUDA events released on every exit path
-struct EventList {
-  std::vector<cudaEvent_t> ev;
-  int add(cudaEvent_t* out) {
-    cudaEvent_t e;
-    MPQC_T_CUDA(cudaEventCreate(&e));
-    ev.push_back(e);
-    *out = e;
+// device allocation released on every exit path
+struct DevBuf {
+  double* p = nullptr;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { cudaFree(p); }
+  int alloc(size_t doubles) {
+    MPQC_T_CUDA(cudaMalloc(&p, std::max<size_t>(doubles, 1) * sizeof(double)));
     return MPQC_T_OK;
   }
-  ~EventList() {
-    for (auto e : ev) cudaEventDestroy(e);
-  }
 };
 
-// copy host->device (or alias a device pointer) for the small/medium inputs
+// this worker's place in the (T) communicator; nranks == 1 means "no exchange"
+struct CommView {
+  int rank = 0, nranks = 1;
+  NcclApi::comm_t comm = nullptr;
+  double* scratch = nullptr;
+};
+
+inline size_t share_of(size_t n, int nranks) { return (n + (size_t)nranks - 1) / (size_t)nranks; }
+inline size_t padded_count(size_t n, int nranks) { return share_of(n, nranks) * (size_t)nranks; }
+
+// Puts host tensor src[n] into dst on EVERY rank (dst capacity >= padded_count(n, nranks)): this rank moves only its
+// 1/nranks share over its own PCIe link, then one in-place ncclAllGather over NVLink completes the tensor.  With
+// nranks == 1 it is a plain host->device copy.  The collective is issued even if the local copy failed, so that peer
+// ranks never wait for a rank that dropped out.
+int replicate_from_host(const CommView& cv, double* dst, const double* src, size_t n, cudaStream_t st, int64_t* h2d) {
+  if (n == 0) return MPQC_T_OK;
+  if (cv.nranks <= 1) {
+    MPQC_T_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (h2d) *h2d += (int64_t)(n * sizeof(double));
+    return MPQC_T_OK;
+  }
+  const size_t cnt = share_of(n, cv.nranks);
+  const size_t lo = std::min(n, cnt * (size_t)cv.rank), hi = std::min(n, lo + cnt);
+  int rc = MPQC_T_OK;
+  if (hi > lo) {
+    rc = cuda_status(cudaMemcpyAsync(dst + lo, src + lo, (hi - lo) * sizeof(double), cudaMemcpyHostToDevice, st),
+                     "cudaMemcpyAsync(host share)", __FILE__, __LINE__);
+    if (h2d) *h2d += (int64_t)((hi - lo) * sizeof(double));
+  }
+  const NcclApi& nc = nccl_api();
+  int r = nc.AllGather(dst + cnt * (size_t)cv.rank, dst, cnt, kNcclFloat64, cv.comm, st);
+  if (rc == MPQC_T_OK) rc = nccl_status(r, "ncclAllGather(input replication)", __FILE__, __LINE__);
+  return rc;
+}
+
+// host tensor -> device copy (sharded + all-gathered when a communicator is present), or an alias of a device pointer
 struct Staged {
   const double* ptr = nullptr;
-  double* owned = nullptr;
-  ~Staged() { cudaFree(owned); }
+  DevBuf owned;
 };
 
-int stage_in(Staged& s, const double* src, size_t n, bool on_device, cudaStream_t st, int64_t* h2d) {
+int stage_in(Staged& s, const double* src, size_t n, bool on_device, const CommView& cv, cudaStream_t st, int64_t* h2d) {
   if (on_device) {
     s.ptr = src;
     return MPQC_T_OK;
   }
-  MPQC_T_CUDA(cudaMalloc(&s.owned, std::max<size_t>(n, 1) * sizeof(double)));
-  MPQC_T_CUDA(cudaMemcpyAsync(s.owned, src, n * sizeof(double), cudaMemcpyHostToDevice, st));
-  if (h2d) *h2d += (int64_t)(n * sizeof(double));
-  s.ptr = s.owned;
+  MPQC_T_TRY(s.owned.alloc(padded_count(n, cv.nranks)));
+  MPQC_T_TRY(replicate_from_host(cv, s.owned.p, src, n, st, h2d));
+  s.ptr = s.owned.p;
   return MPQC_T_OK;
 }
 
-int upload_impl(mpqc_t_handle* h, const mpqc_t_problem* p, bool on_device, mpqc_t_stats* stats) {
+int upload_impl(mpqc_t_handle* h, const mpqc_t_problem* p, bool on_device, const CommView& cv, mpqc_t_stats* stats) {
   const int64_t o = h->o, v = h->v, Kp = h->Kp;
   cudaStream_t st = h->stream;
   int64_t launches = 0, h2d = 0;
   const double t0 = now_s();
   double t_copy = 0.0;
+  // Ordering contract (include/mpqc_t.h): device-resident inputs may have been produced on any stream of the caller;
+  // the handle's stream is non-blocking, so wait for the whole device before reading them.
+  if (on_device) MPQC_T_CUDA(cudaDeviceSynchronize());
 
   MPQC_T_CUDA(cudaMemsetAsync(h->A, 0, (size_t)o * v * v * Kp * sizeof(double), st));
   if (h->flat) MPQC_T_CUDA(cudaMemsetAsync(h->AT, 0, (size_t)o * v * v * Kp * sizeof(double), st));
@@ -394,19 +424,16 @@ int upload_impl(mpqc_t_handle* h, const mpqc_t_problem* p, bool on_device, mpqc_
 
   {
     double tc = now_s();
-    if (!on_device) {
-      MPQC_T_CUDA(cudaMemcpyAsync(h->eps_occ, p->eps_occ, o * sizeof(double), cudaMemcpyHostToDevice, st));
-      MPQC_T_CUDA(cudaMemcpyAsync(h->eps_vir, p->eps_vir, v * sizeof(double), cudaMemcpyHostToDevice, st));
-      h2d += (o + v) * 8;
-    } else {
-      MPQC_T_CUDA(cudaMemcpyAsync(h->eps_occ, p->eps_occ, o * sizeof(double), cudaMemcpyDeviceToDevice, st));
-      MPQC_T_CUDA(cudaMemcpyAsync(h->eps_vir, p->eps_vir, v * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    }
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    MPQC_T_CUDA(cudaMemcpyAsync(h->eps_occ, p->eps_occ, o * sizeof(double), kind, st));
+    MPQC_T_CUDA(cudaMemcpyAsync(h->eps_vir, p->eps_vir, v * sizeof(double), kind, st));
+    if (!on_device) h2d += (o + v) * 8;
     Staged t1, t2, gabij, gaijk;
-    MPQC_T_TRY(stage_in(t1, p->t1, (size_t)v * o, on_device, st, &h2d));
-    MPQC_T_TRY(stage_in(t2, p->t2, (size_t)v * v * o * o, on_device, st, &h2d));
-    MPQC_T_TRY(stage_in(gabij, p->g_abij, (size_t)v * v * o * o, on_device, st, &h2d));
-    MPQC_T_TRY(stage_in(gaijk, p->g_aijk, (size_t)v * o * o * o, on_device, st, &h2d));
+    CommView solo;   // the tiny t1 is copied whole by every rank
+    MPQC_T_TRY(stage_in(t1, p->t1, (size_t)v * o, on_device, solo, st, &h2d));
+    MPQC_T_TRY(stage_in(t2, p->t2, (size_t)v * v * o * o, on_device, cv, st, &h2d));
+    MPQC_T_TRY(stage_in(gabij, p->g_abij, (size_t)v * v * o * o, on_device, cv, st, &h2d));
+    MPQC_T_TRY(stage_in(gaijk, p->g_aijk, (size_t)v * o * o * o, on_device, cv, st, &h2d));
     if (!on_device) {
       MPQC_T_CUDA(cudaStreamSynchronize(st));
       t_copy += now_s() - tc;
@@ -433,36 +460,37 @@ int upload_impl(mpqc_t_handle* h, const mpqc_t_problem* p, bool on_device, mpqc_
       MPQC_T_TRY(launch_transpose(st, p->g_abci, h->AT, v, v, v * o, o, v * Kp, v * v * Kp, Kp, &launches));
     MPQC_T_CUDA(cudaStreamSynchronize(st));
   } else {
+    // slabs of whole kap rows; each slab crosses PCIe once in total (1/nranks of it per rank) and is completed by an
+    // all-gather, then transposed into place.  Two slabs so that the copy of the next one is queued while the
+    // transposes of the current one run.
     const size_t row = (size_t)v * v * o;  // doubles per kap
-    int64_t slab = std::max<int64_t>(1, std::min<int64_t>(v, (int64_t)((1ull << 30) / (row * 8 + 1)) + 1));
-    double* buf[2] = {nullptr, nullptr};
-    cudaEvent_t done[2];
-    for (int s = 0; s < 2; ++s) {
-      MPQC_T_CUDA(cudaMalloc(&buf[s], (size_t)slab * row * sizeof(double)));
-      MPQC_T_CUDA(cudaEventCreateWithFlags(&done[s], cudaEventDisableTiming));
-    }
+    const size_t slab_bytes = cv.nranks > 1 ? (size_t(2) << 30) : (size_t(1) << 30);
+    const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(v, (int64_t)(slab_bytes / (row * 8 + 1)) + 1));
+    DevBuf buf[2];
+    for (int s = 0; s < 2; ++s) MPQC_T_TRY(buf[s].alloc(padded_count((size_t)slab * row, cv.nranks)));
+    EventList events;               // copy (+ all-gather) time of every slab, device-timed on the handle's stream
+    std::vector<cudaEvent_t> ev;
     int which = 0;
-    int rc = MPQC_T_OK;
-    for (int64_t d0 = 0; d0 < v && rc == MPQC_T_OK; d0 += slab, which ^= 1) {
-      int64_t nd = std::min(slab, v - d0);
-      double tc = now_s();
-      cudaEventSynchronize(done[which]);
-      cudaError_t e = cudaMemcpyAsync(buf[which], p->g_abci + (size_t)d0 * row, (size_t)nd * row * sizeof(double),
-                                      cudaMemcpyHostToDevice, st);
-      if (e != cudaSuccess) { rc = cuda_status(e, "cudaMemcpyAsync(g_abci slab)", __FILE__, __LINE__); break; }
-      t_copy += now_s() - tc;
-      h2d += (int64_t)(nd * row * 8);
-      rc = launch_transpose(st, buf[which], h->A + d0, nd, v, v * o, o, Kp, v * v * Kp, v * Kp, &launches);
-      if (rc == MPQC_T_OK && h->flat)
-        rc = launch_transpose(st, buf[which], h->AT + d0, nd, v, v * o, o, v * Kp, v * v * Kp, Kp, &launches);
-      cudaEventRecord(done[which], st);
+    for (int64_t d0 = 0; d0 < v; d0 += slab, which ^= 1) {
+      const int64_t nd = std::min(slab, v - d0);
+      cudaEvent_t e0, e1;
+      MPQC_T_TRY(events.add(&e0));
+      MPQC_T_TRY(events.add(&e1));
+      MPQC_T_CUDA(cudaEventRecord(e0, st));
+      MPQC_T_TRY(replicate_from_host(cv, buf[which].p, p->g_abci + (size_t)d0 * row, (size_t)nd * row, st, &h2d));
+      MPQC_T_CUDA(cudaEventRecord(e1, st));
+      ev.push_back(e0);
+      ev.push_back(e1);
+      MPQC_T_TRY(launch_transpose(st, buf[which].p, h->A + d0, nd, v, v * o, o, Kp, v * v * Kp, v * Kp, &launches));
+      if (h->flat)
+        MPQC_T_TRY(launch_transpose(st, buf[which].p, h->AT + d0, nd, v, v * o, o, v * Kp, v * v * Kp, Kp, &launches));
     }
-    cudaStreamSynchronize(st);
-    for (int s = 0; s < 2; ++s) {
-      cudaFree(buf[s]);
-      cudaEventDestroy(done[s]);
+    MPQC_T_CUDA(cudaStreamSynchronize(st));
+    for (size_t q = 0; q + 1 < ev.size(); q += 2) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[q], ev[q + 1]);
+      t_copy += ms * 1e-3;
     }
-    MPQC_T_TRY(rc);
   }
   MPQC_T_CUDA(cudaGetLastError());
   h->uploaded = true;
@@ -490,7 +518,7 @@ int upload_impl(mpqc_t_handle* h, const mpqc_t_problem* p, bool on_device, mpqc_
 // from the three-centre factors (what the reference's [df] formulas evaluate through TiledArray on the host,
 // ccsd_t.h:2210-2244 with is_df()).  These are plain strided-batched library DGEMMs (cuBLAS), one-time, ~2 naux v^3 o
 // FLOPs for each of A and AT; the triples loop itself is unchanged.
-int upload_df_impl(mpqc_t_handle* h, const mpqc_t_df_problem* p, bool on_device, mpqc_t_stats* stats) {
+int upload_df_impl(mpqc_t_handle* h, const mpqc_t_df_problem* p, bool on_device, const CommView& cv, mpqc_t_stats* stats) {
   const int64_t o = h->o, v = h->v, Kp = h->Kp, naux = p->naux;
   cudaStream_t st = h->stream;
   int64_t launches = 0, h2d = 0;
@@ -498,6 +526,7 @@ int upload_df_impl(mpqc_t_handle* h, const mpqc_t_df_problem* p, bool on_device,
   double t_copy = 0.0;
   const BlasApi& bl = blas_api();
   MPQC_T_CHECK(bl.ok, MPQC_T_ERR_CUDA, "density-fitted upload needs libcublas.so.12, which could not be loaded");
+  if (on_device) MPQC_T_CUDA(cudaDeviceSynchronize());   // ordering contract for device-resident inputs (mpqc_t.h)
   if (!h->blas) {
     MPQC_T_BLAS(bl.Create(&h->blas));
     MPQC_T_BLAS(bl.SetStream(h->blas, st));   // pointer mode defaults to host
@@ -512,20 +541,20 @@ int upload_df_impl(mpqc_t_handle* h, const mpqc_t_df_problem* p, bool on_device,
   MPQC_T_CUDA(cudaMemcpyAsync(h->eps_vir, p->eps_vir, v * sizeof(double), kind, st));
   if (!on_device) h2d += (o + v) * 8;
   Staged t1, t2, xab, xij, xai;
-  MPQC_T_TRY(stage_in(t1, p->t1, (size_t)v * o, on_device, st, &h2d));
-  MPQC_T_TRY(stage_in(t2, p->t2, (size_t)v * v * o * o, on_device, st, &h2d));
-  MPQC_T_TRY(stage_in(xab, p->x_ab, (size_t)naux * v * v, on_device, st, &h2d));
-  MPQC_T_TRY(stage_in(xij, p->x_ij, (size_t)naux * o * o, on_device, st, &h2d));
-  MPQC_T_TRY(stage_in(xai, p->x_ai, (size_t)naux * v * o, on_device, st, &h2d));
+  CommView solo;
+  MPQC_T_TRY(stage_in(t1, p->t1, (size_t)v * o, on_device, solo, st, &h2d));
+  MPQC_T_TRY(stage_in(t2, p->t2, (size_t)v * v * o * o, on_device, cv, st, &h2d));
+  MPQC_T_TRY(stage_in(xab, p->x_ab, (size_t)naux * v * v, on_device, cv, st, &h2d));
+  MPQC_T_TRY(stage_in(xij, p->x_ij, (size_t)naux * o * o, on_device, solo, st, &h2d));
+  MPQC_T_TRY(stage_in(xai, p->x_ai, (size_t)naux * v * o, on_device, cv, st, &h2d));
   if (!on_device) {
     MPQC_T_CUDA(cudaStreamSynchronize(st));
     t_copy += now_s() - tc;
   }
   // XaiT[x][K][a] = Xai[K][a][x]  (unit stride on the virtual index for the GEMMs below)
-  double* xait = nullptr;
-  MPQC_T_CUDA(cudaMalloc(&xait, (size_t)o * naux * v * sizeof(double)));
-  Staged xait_owner;
-  xait_owner.owned = xait;
+  DevBuf xait_owner;
+  MPQC_T_TRY(xait_owner.alloc((size_t)o * naux * v));
+  double* xait = xait_owner.p;
   // in[kap = K][mid = a][j = x] -> out[x * naux*v + K * v + a]: generic transpose wants kap last, so treat
   // (K,a) flattened as kap: in[(K a)][1][x] -> out[x][(K a)]
   MPQC_T_TRY(launch_transpose(st, xai.ptr, xait, naux * v, 1, o, 1, naux * v, 0, 0, &launches));
@@ -575,9 +604,10 @@ int upload_df_impl(mpqc_t_handle* h, const mpqc_t_df_problem* p, bool on_device,
 }
 
 // Run an explicit list of units (indices into the global enumeration).  unit_e_host[n] receives the
-// weighted per-unit energies.  Synchronises the stream before returning.
-int run_units(mpqc_t_handle* h, const std::vector<int>& all_triples, const int64_t* units, int64_t n, int batch,
-              double* unit_e_host, mpqc_t_stats* stats, bool profile) {
+// weighted per-unit energies.  vblock_dev (optional, [ntt] on the device, zeroed by the caller) accumulates the
+// decomposition of the same energy over virtual-block triples.  Synchronises the stream before returning.
+int run_units(mpqc_t_handle* h, const UnitIndex& ux, const int64_t* units, int64_t n, int batch,
+              double* unit_e_host, mpqc_t_stats* stats, bool profile, double* vblock_dev = nullptr) {
   if (n == 0) return MPQC_T_OK;
   MPQC_T_CUDA(cudaSetDevice(h->device));
   if (batch <= 0) batch = auto_batch(h);
@@ -590,8 +620,7 @@ int run_units(mpqc_t_handle* h, const std::vector<int>& all_triples, const int64
   MPQC_T_TRY(ensure_work(h, batch));
   MPQC_T_TRY(ensure_units(h, n));
   std::vector<int> tri((size_t)n * 3);
-  for (int64_t u = 0; u < n; ++u)
-    for (int c = 0; c < 3; ++c) tri[3 * u + c] = all_triples[3 * units[u] + c];
+  for (int64_t u = 0; u < n; ++u) ux.triple(units[u], tri[3 * u], tri[3 * u + 1], tri[3 * u + 2]);
   MPQC_T_CUDA(cudaMemcpyAsync(h->triples_dev, tri.data(), tri.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
 
   const int64_t nbatches = (n + batch - 1) / batch;
@@ -616,6 +645,12 @@ int run_units(mpqc_t_handle* h, const std::vector<int>& all_triples, const int64
     MPQC_T_TRY(launch_energy(h, nb, h->triples_dev + 3 * off, h->unit_e_dev + off));
     if (profile) cudaEventRecord(ev[3 * bi + 2], h->stream);
     launches += 3;
+    if (vblock_dev) {
+      t_energy_vblock_kernel<<<(h->ntt + 255) / 256, 256, 0, h->stream>>>(h->partial, h->ntt, nb,
+                                                                        h->triples_dev + 3 * off, vblock_dev);
+      MPQC_T_CUDA(cudaGetLastError());
+      ++launches;
+    }
   }
   MPQC_T_CUDA(cudaEventRecord(e_end, h->stream));
   MPQC_T_CUDA(cudaMemcpyAsync(unit_e_host, h->unit_e_dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -648,6 +683,33 @@ int run_units(mpqc_t_handle* h, const std::vector<int>& all_triples, const int64
   return MPQC_T_OK;
 }
 
+// sum-all-reduce of n doubles held on the host through the member's pre-allocated device scratch (chunked), so the
+// collective itself never allocates.  Result overwrites x on every rank.
+int allreduce_host_vector(const CommView& cv, double* x, size_t n, cudaStream_t st) {
+  const NcclApi& nc = nccl_api();
+  for (size_t c0 = 0; c0 < n; c0 += kCommScratchDoubles) {
+    const size_t cn = std::min(kCommScratchDoubles, n - c0);
+    MPQC_T_CUDA(cudaMemcpyAsync(cv.scratch, x + c0, cn * sizeof(double), cudaMemcpyHostToDevice, st));
+    MPQC_T_NCCL(nc.AllReduce(cv.scratch, cv.scratch, cn, kNcclFloat64, kNcclSum, cv.comm, st));
+    MPQC_T_CUDA(cudaMemcpyAsync(x + c0, cv.scratch, cn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    MPQC_T_CUDA(cudaStreamSynchronize(st));
+  }
+  return MPQC_T_OK;
+}
+
+// Agreement on a status among all ranks: returns the number of ranks that reported a failure (or -1 when the
+// collective itself failed).  Every rank calls it at the same points, whatever happened locally, so a rank that ran
+// out of memory makes the others return an error instead of leaving them blocked in a later collective.
+int count_failed_ranks(const CommView& cv, int local_rc, cudaStream_t st) {
+  if (cv.nranks <= 1) return local_rc != MPQC_T_OK ? 1 : 0;
+  double flag = local_rc != MPQC_T_OK ? 1.0 : 0.0;
+  const std::string keep = last_error_string();
+  int rc = allreduce_host_vector(cv, &flag, 1, st);
+  if (local_rc != MPQC_T_OK) last_error_string() = keep;
+  if (rc != MPQC_T_OK) return -1;
+  return (int)(flag + 0.5);
+}
+
 int validate_problem(const mpqc_t_problem* p) {
   MPQC_T_CHECK(p != nullptr, MPQC_T_ERR_BAD_ARG, "problem is NULL");
   MPQC_T_CHECK(p->o >= 1 && p->v >= 1, MPQC_T_ERR_BAD_ARG, "o and v must be >= 1");
@@ -664,7 +726,7 @@ int validate_problem(const mpqc_t_problem* p) {
 // -------------------------------------------------------------------------------------------------
 extern "C" {
 
-const char* mpqc_t_version(void) { return "mpqc_t_cuda 0.1 (sm_100a, abi 1)"; }
+const char* mpqc_t_version(void) { return "mpqc_t_cuda 0.2 (sm_100a, abi 2)"; }
 
 const char* mpqc_t_strerror(int status) {
   switch (status) {
@@ -688,27 +750,15 @@ int64_t mpqc_t_triple_count(int64_t o) {
 
 int mpqc_t_triple_of_unit(int64_t o, int64_t unit, int32_t* i, int32_t* j, int32_t* k) {
   MPQC_T_CHECK(i && j && k, MPQC_T_ERR_BAD_ARG, "NULL output");
+  MPQC_T_CHECK(o >= 1 && o <= 4096, MPQC_T_ERR_BAD_ARG, "need 1 <= o <= 4096");
   MPQC_T_CHECK(unit >= 0 && unit < mpqc_t_triple_count(o), MPQC_T_ERR_BAD_ARG, "unit out of range");
-  int64_t u = 0;
-  for (int64_t a = 0; a < o; ++a) {
-    // units with first index a: (a+1)(a+2)/2 - 1
-    int64_t na = (a + 1) * (a + 2) / 2 - 1;
-    if (unit < u + na) {
-      int64_t r = unit - u;
-      for (int64_t b = 0; b <= a; ++b) {
-        int64_t nb = (b + 1) - ((b == a) ? 1 : 0);
-        if (r < nb) {
-          *i = (int32_t)a;
-          *j = (int32_t)b;
-          *k = (int32_t)r;
-          return MPQC_T_OK;
-        }
-        r -= nb;
-      }
-    }
-    u += na;
-  }
-  return fail(MPQC_T_ERR_INTERNAL, "triple enumeration", __FILE__, __LINE__);
+  const UnitIndex ux(o);
+  int a, b, c;
+  ux.triple(unit, a, b, c);
+  *i = a;
+  *j = b;
+  *k = c;
+  return MPQC_T_OK;
 }
 
 double mpqc_t_flops(int64_t o, int64_t v) { return 2.0 * (double)o * o * o * (double)v * v * v * (double)(v + o); }
@@ -779,6 +829,18 @@ int mpqc_t_create(mpqc_t_handle** out, int64_t o, int64_t v, int32_t device) {
       const char* env = getenv("MPQC_T_FLAT");
       h->flat = (2.0 * a_bytes + rest) < 0.75 * (double)free_b ? 1 : 0;
       if (env) h->flat = atoi(env) != 0;
+      // feasibility: the accepted (o, v) range is far wider than what one device can hold.  Refuse here, with the
+      // numbers, instead of failing inside some later cudaMalloc: resident operands + the W workspace of ONE triple.
+      const double w_one = 3.0 * (double)v * v * (double)roundup(v, 16) * 8.0;
+      const double need = a_bytes * (h->flat ? 2.0 : 1.0) + (rest - 8e9) + w_one;
+      if (need > 0.98 * (double)free_b) {
+        char buf[320];
+        snprintf(buf, sizeof(buf),
+                 "problem o=%lld v=%lld needs %.1f GB of device memory (operands %.1f GB + W workspace %.1f GB per triple) "
+                 "but only %.1f GB are free on device %d",
+                 (long long)o, (long long)v, need * 1e-9, (need - w_one) * 1e-9, w_one * 1e-9, (double)free_b * 1e-9, device);
+        return fail(MPQC_T_ERR_OOM, buf, __FILE__, __LINE__);
+      }
     }
     MPQC_T_CUDA(cudaMalloc(&h->A, (size_t)o * v * v * h->Kp * sizeof(double)));
     if (h->flat) MPQC_T_CUDA(cudaMalloc(&h->AT, (size_t)o * v * v * h->Kp * sizeof(double)));
@@ -847,37 +909,141 @@ int mpqc_t_upload(mpqc_t_handle* h, const mpqc_t_problem* p, int32_t on_device, 
   MPQC_T_TRY(validate_problem(p));
   MPQC_T_CHECK(p->o == h->o && p->v == h->v, MPQC_T_ERR_BAD_ARG, "problem dimensions differ from the handle's");
   MPQC_T_CUDA(cudaSetDevice(h->device));
-  return upload_impl(h, p, on_device != 0, stats);
+  return upload_impl(h, p, on_device != 0, CommView(), stats);
 }
 
-int mpqc_t_run(mpqc_t_handle* h, int64_t first, int64_t stride, int64_t count, int32_t batch, double* partial_e,
-               double* unit_e, mpqc_t_stats* stats) {
+static int run_range(mpqc_t_handle* h, int64_t first, int64_t stride, int64_t count, int32_t batch, double* partial_e,
+                     double* unit_e, double* vblock_e, mpqc_t_stats* stats) {
   MPQC_T_CHECK(h != nullptr && partial_e != nullptr, MPQC_T_ERR_BAD_ARG, "handle or output is NULL");
   MPQC_T_CHECK(h->uploaded, MPQC_T_ERR_BAD_ARG, "mpqc_t_upload has not been called on this handle");
   if (stride <= 0) stride = 1;
-  const int64_t nt = mpqc_t_triple_count(h->o);
+  const UnitIndex ux(h->o);
+  const int64_t nt = ux.count();
   MPQC_T_CHECK(first >= 0, MPQC_T_ERR_BAD_ARG, "unit_first < 0");
   int64_t avail = first < nt ? (nt - first + stride - 1) / stride : 0;
   if (count < 0 || count > avail) count = avail;
   *partial_e = 0.0;
   const double t0 = now_s();
+  MPQC_T_CUDA(cudaSetDevice(h->device));
+  DevBuf vb;
+  if (vblock_e) {
+    MPQC_T_TRY(vb.alloc((size_t)h->ntt));
+    MPQC_T_CUDA(cudaMemsetAsync(vb.p, 0, (size_t)h->ntt * sizeof(double), h->stream));
+  }
   if (count > 0) {
-    std::vector<int> all;
-    build_triple_list(h->o, all);
     std::vector<int64_t> units((size_t)count);
     for (int64_t u = 0; u < count; ++u) units[u] = first + u * stride;
     std::vector<double> ue((size_t)count);
-    MPQC_T_TRY(run_units(h, all, units.data(), count, batch, ue.data(), stats, getenv("MPQC_T_PROFILE") != nullptr));
+    MPQC_T_TRY(run_units(h, ux, units.data(), count, batch, ue.data(), stats, getenv("MPQC_T_PROFILE") != nullptr, vb.p));
     double s = 0.0;
     for (int64_t u = 0; u < count; ++u) s += ue[u];   // fixed unit order -> deterministic
     *partial_e = s;
     if (unit_e) memcpy(unit_e, ue.data(), (size_t)count * sizeof(double));
+  }
+  if (vblock_e) {
+    MPQC_T_CUDA(cudaMemcpyAsync(vblock_e, vb.p, (size_t)h->ntt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    MPQC_T_CUDA(cudaStreamSynchronize(h->stream));
   }
   if (stats) {
     stats->seconds_total += now_s() - t0;
     stats->ngpu = 1;
   }
   return MPQC_T_OK;
+}
+
+int mpqc_t_run(mpqc_t_handle* h, int64_t first, int64_t stride, int64_t count, int32_t batch, double* partial_e,
+               double* unit_e, mpqc_t_stats* stats) {
+  return run_range(h, first, stride, count, batch, partial_e, unit_e, nullptr, stats);
+}
+
+int mpqc_t_run_comm(mpqc_t_handle* h, mpqc_t_comm* c, int64_t first, int64_t stride, int64_t count, int32_t batch,
+                    double* total_e, double* unit_e, mpqc_t_stats* stats) {
+  MPQC_T_CHECK(h != nullptr && c != nullptr && total_e != nullptr, MPQC_T_ERR_BAD_ARG, "handle, communicator or output is NULL");
+  MPQC_T_CHECK(h->uploaded, MPQC_T_ERR_BAD_ARG, "mpqc_t_upload has not been called on this handle");
+  MPQC_T_CHECK(c->members.size() == 1 && c->members[0].device == h->device, MPQC_T_ERR_BAD_ARG,
+               "mpqc_t_run_comm needs a rank-mode communicator whose device is the handle's");
+  if (stride <= 0) stride = 1;
+  const UnitIndex ux(h->o);
+  const int64_t nt = ux.count();
+  MPQC_T_CHECK(first >= 0, MPQC_T_ERR_BAD_ARG, "unit_first < 0");
+  const int64_t avail = first < nt ? (nt - first + stride - 1) / stride : 0;
+  if (count < 0 || count > avail) count = avail;
+  const CommMember& m = c->members[0];
+  const int R = c->nranks, r = m.rank;
+  *total_e = 0.0;
+  const double t0 = now_s();
+  MPQC_T_CUDA(cudaSetDevice(h->device));
+  // this rank's share: job positions r, r+R, ...
+  const int64_t mine = count > r ? (count - r + R - 1) / R : 0;
+  std::vector<int64_t> units((size_t)mine);
+  for (int64_t q = 0; q < mine; ++q) units[(size_t)q] = first + (r + q * R) * stride;
+  std::vector<double> ue_mine((size_t)mine);
+  int rc = run_units(h, ux, units.data(), mine, batch, ue_mine.data(), stats, getenv("MPQC_T_PROFILE") != nullptr);
+  // Job-length vector on the device: own units at their job positions (strided device copy from the per-unit results
+  // run_units left in h->unit_e_dev), zeros elsewhere; one ncclAllReduce on the handle's stream completes it on every
+  // rank (x + 0 + ... + 0 is exact).  Reached also after a local failure, with a raised status word, so that no peer
+  // blocks (the vector lives in the communicator's pre-allocated scratch when it fits).
+  std::vector<double> all((size_t)count + 1, 0.0);
+  if (R > 1) {
+    const NcclApi& nc = nccl_api();
+    const bool fits = (size_t)count + 1 <= kCommScratchDoubles;
+    if (fits) {
+      int r2 = cuda_status(cudaMemsetAsync(m.scratch, 0, ((size_t)count + 1) * sizeof(double), h->stream), "memset", __FILE__, __LINE__);
+      if (rc == MPQC_T_OK && r2 == MPQC_T_OK && mine > 0)
+        r2 = cuda_status(cudaMemcpy2DAsync(m.scratch + r, (size_t)R * sizeof(double), h->unit_e_dev, sizeof(double),
+                                           sizeof(double), (size_t)mine, cudaMemcpyDeviceToDevice, h->stream),
+                         "cudaMemcpy2DAsync(unit energies)", __FILE__, __LINE__);
+      if (rc != MPQC_T_OK || r2 != MPQC_T_OK) {
+        const double one = 1.0;
+        cudaMemcpyAsync(m.scratch + count, &one, sizeof(double), cudaMemcpyHostToDevice, h->stream);
+      }
+      const std::string keep = last_error_string();
+      int r3 = nccl_status(nc.AllReduce(m.scratch, m.scratch, (size_t)count + 1, kNcclFloat64, kNcclSum, m.comm, h->stream),
+                           "ncclAllReduce(unit energies)", __FILE__, __LINE__);
+      if (r3 == MPQC_T_OK)
+        r3 = cuda_status(cudaMemcpyAsync(all.data(), m.scratch, ((size_t)count + 1) * sizeof(double), cudaMemcpyDeviceToHost, h->stream),
+                         "cudaMemcpyAsync(summed unit energies)", __FILE__, __LINE__);
+      if (r3 == MPQC_T_OK) r3 = cuda_status(cudaStreamSynchronize(h->stream), "cudaStreamSynchronize", __FILE__, __LINE__);
+      if (rc != MPQC_T_OK) last_error_string() = keep;
+      if (rc == MPQC_T_OK) rc = r2 != MPQC_T_OK ? r2 : r3;
+    } else {
+      for (int64_t q = 0; q < mine && rc == MPQC_T_OK; ++q) all[(size_t)(r + q * R)] = ue_mine[(size_t)q];
+      all[(size_t)count] = rc == MPQC_T_OK ? 0.0 : 1.0;
+      CommView cv;
+      cv.rank = r;
+      cv.nranks = R;
+      cv.comm = m.comm;
+      cv.scratch = m.scratch;
+      const std::string keep = last_error_string();
+      const int r3 = allreduce_host_vector(cv, all.data(), all.size(), h->stream);
+      if (rc != MPQC_T_OK) last_error_string() = keep;
+      if (rc == MPQC_T_OK) rc = r3;
+    }
+    if (rc == MPQC_T_OK && all[(size_t)count] > 0.5)
+      rc = fail(MPQC_T_ERR_INTERNAL, "another rank of the (T) communicator failed during the triples loop", __FILE__, __LINE__);
+    if (stats) {
+      stats->bytes_d2h += ((int64_t)count + 1) * 8;
+      stats->kernel_launches += 1;   // the all-reduce
+    }
+  } else {
+    for (int64_t q = 0; q < mine; ++q) all[(size_t)q] = ue_mine[(size_t)q];
+  }
+  MPQC_T_TRY(rc);
+  double s = 0.0;
+  for (int64_t u = 0; u < count; ++u) s += all[(size_t)u];   // job order: identical on every rank and for every R
+  *total_e = s;
+  if (unit_e) memcpy(unit_e, all.data(), (size_t)count * sizeof(double));
+  if (stats) {
+    stats->seconds_total += now_s() - t0;
+    stats->ngpu = 1;
+  }
+  return MPQC_T_OK;
+}
+
+int mpqc_t_run_vblocks(mpqc_t_handle* h, int64_t first, int64_t stride, int64_t count, int32_t batch, double* partial_e,
+                       double* unit_e, double* vblock_e, mpqc_t_stats* stats) {
+  MPQC_T_CHECK(vblock_e != nullptr, MPQC_T_ERR_BAD_ARG, "vblock_e is NULL");
+  return run_range(h, first, stride, count, batch, partial_e, unit_e, vblock_e, stats);
 }
 
 int mpqc_t_debug_w(mpqc_t_handle* h, int32_t i, int32_t j, int32_t k, double* w_host) {
@@ -908,196 +1074,185 @@ int mpqc_t_debug_w(mpqc_t_handle* h, int32_t i, int32_t j, int32_t k, double* w_
 
 namespace {
 
-typedef std::function<int(mpqc_t_handle*, mpqc_t_stats*)> UploadFn;
+typedef std::function<int(mpqc_t_handle*, const CommView&, mpqc_t_stats*)> UploadFn;
 
-// Shared driver of the one-shot entry points: shard the units over this process' GPUs (static share + work-stealing
-// tail), run them, sum the partial energies (host, or one ncclAllReduce).  `upload` puts the inputs on one handle.
+// Shared driver of the one-shot entry points.  The job is the unit list  first, first+stride, ... (count of them);
+// it is sharded over the W workers of the communicator (worker w takes job positions w, w+W, ...; when every worker
+// lives in this process the last 1/8 is handed out by an atomic counter instead -- work stealing), each worker
+// uploads/replicates the inputs onto its GPU, runs its units, and the per-unit energies are summed: on the host
+// when no communicator is involved, else by one ncclAllReduce over the unit-energy vector.
 int energy_impl(const int64_t prob_o, const int64_t prob_v, const UploadFn& upload, const mpqc_t_options* opt_in,
-                double* e_t, mpqc_t_stats* stats_out) {
-  struct { int64_t o, v; } pp = {prob_o, prob_v};
-  const auto* p = &pp;
+                mpqc_t_comm* comm_in, double* e_t, mpqc_t_stats* stats_out) {
   mpqc_t_options opt;
   memset(&opt, 0, sizeof(opt));
   if (opt_in) opt = *opt_in;
-  const int ngpu = opt.ngpu > 0 ? opt.ngpu : 1;
-  MPQC_T_CHECK(!(opt.inputs_on_device && ngpu != 1), MPQC_T_ERR_BAD_ARG, "inputs_on_device requires ngpu == 1");
   const int ndev = mpqc_t_device_count();
   MPQC_T_CHECK(ndev > 0, MPQC_T_ERR_NO_DEVICE, "no CUDA device visible; the (T) path has no CPU fallback");
-  std::vector<int> devs(ngpu);
-  for (int g = 0; g < ngpu; ++g) {
-    devs[g] = opt.device_ids ? opt.device_ids[g] : g;
-    MPQC_T_CHECK(devs[g] >= 0 && devs[g] < ndev, MPQC_T_ERR_BAD_ARG, "device ordinal out of range");
+
+  // ---- who works: the communicator's members that live here, or opt.ngpu devices without a communicator ----
+  struct TempComm {
+    mpqc_t_comm* c = nullptr;
+    ~TempComm() { mpqc_t_comm_destroy(c); }
+  } temp;
+  mpqc_t_comm* comm = comm_in;
+  if (!comm && opt.use_nccl && opt.ngpu > 1) {
+    // one-shot convenience: a communicator that lives for this call only (its set-up costs seconds; hosts that call
+    // more than once, or that can prepare ahead of time, should hold a persistent mpqc_t_comm)
+    MPQC_T_TRY(mpqc_t_comm_create_local(&temp.c, opt.ngpu, opt.device_ids));
+    comm = temp.c;
   }
+  std::vector<CommView> views;
+  std::vector<int> devs;
+  int nranks = 1;
+  if (comm) {
+    nranks = comm->nranks;
+    for (const CommMember& m : comm->members) {
+      CommView cv;
+      cv.rank = m.rank;
+      cv.nranks = comm->nranks;
+      cv.comm = m.comm;
+      cv.scratch = m.scratch;
+      views.push_back(cv);
+      devs.push_back(m.device);
+    }
+  } else {
+    const int ngpu = opt.ngpu > 0 ? opt.ngpu : 1;
+    for (int g = 0; g < ngpu; ++g) {
+      const int d = opt.device_ids ? opt.device_ids[g] : g;
+      MPQC_T_CHECK(d >= 0 && d < ndev, MPQC_T_ERR_BAD_ARG, "device ordinal out of range");
+      views.push_back(CommView());
+      devs.push_back(d);
+    }
+  }
+  const int nlocal = (int)views.size();
+  const bool exchange = comm != nullptr && nranks > 1;
+  MPQC_T_CHECK(!(opt.inputs_on_device && nlocal != 1), MPQC_T_ERR_BAD_ARG,
+               "inputs_on_device requires one device per process");
   const double t0 = now_s();
   mpqc_t_stats stats;
   memset(&stats, 0, sizeof(stats));
 
-  // this process' shard of the unit list
-  const int64_t nt = mpqc_t_triple_count(p->o);
-  int64_t stride = opt.unit_stride > 0 ? opt.unit_stride : 1;
+  // ---- the job and its split ----
+  const UnitIndex ux(prob_o);
+  const int64_t nt = ux.count();
+  const int64_t stride = opt.unit_stride > 0 ? opt.unit_stride : 1;
   MPQC_T_CHECK(opt.unit_first >= 0, MPQC_T_ERR_BAD_ARG, "unit_first < 0");
-  int64_t avail = opt.unit_first < nt ? (nt - opt.unit_first + stride - 1) / stride : 0;
-  int64_t count = (opt.unit_count < 0 || opt.unit_count > avail) ? avail : opt.unit_count;
-  std::vector<int64_t> units((size_t)count);
-  for (int64_t u = 0; u < count; ++u) units[u] = opt.unit_first + u * stride;
+  const int64_t avail = opt.unit_first < nt ? (nt - opt.unit_first + stride - 1) / stride : 0;
+  const int64_t count = (opt.unit_count < 0 || opt.unit_count > avail) ? avail : opt.unit_count;
   std::vector<double> unit_e((size_t)count, 0.0);   // each slot is written by exactly one worker thread
-  std::vector<int> all;
-  build_triple_list(p->o, all);
-
-  // static share first (unit u -> gpu u % ngpu for the first ~7/8), then a shared work-stealing tail
-  std::vector<mpqc_t_stats> gstats(ngpu);
-  std::vector<int> rcs(ngpu, MPQC_T_OK);
-  std::vector<std::string> msgs(ngpu);
-  std::atomic<int64_t> tail_next;
-  const int64_t static_n = ngpu > 1 ? (count / 8) * 7 / ngpu * ngpu : count;
-  tail_next.store(static_n);
+  const int W = comm ? nranks : nlocal;              // workers over which the job is split
+  const bool all_local = !comm || comm->local;       // work stealing needs shared memory
+  const int64_t static_n = (W > 1 && all_local) ? (count / 8) * 7 / W * W : count;
+  std::atomic<int64_t> tail_next(static_n);
   const bool profile = getenv("MPQC_T_PROFILE") != nullptr;
 
-  // optional NCCL sum: every GPU holds the per-unit energy vector (zeros for units it did not own); one
-  // ncclAllReduce(sum) over NVLink makes it complete everywhere (x + 0 + ... + 0 is exact, so the result is
-  // bit-identical to the host-side gather), then the units are summed in order.
-  const bool use_nccl = opt.use_nccl != 0 && ngpu > 1 && count > 0;
-  std::vector<NcclApi::comm_t> comms(ngpu, nullptr);
-  std::vector<double> nccl_result;
-  std::thread nccl_init_thread;
-  int nccl_init_rc = MPQC_T_OK;       // written by the init thread, read after join
-  std::string nccl_init_msg;
-  double nccl_init_seconds = 0.0;
-  if (use_nccl) {
-    const NcclApi& nc = nccl_api();
-    MPQC_T_CHECK(nc.ok, MPQC_T_ERR_NCCL, "use_nccl requested but libnccl.so.2 could not be loaded");
-    nccl_result.assign((size_t)count, 0.0);
-  }
-  // communicator setup takes seconds (topology discovery + its own allocations): it is started by the last worker
-  // to finish its upload, runs beside the triples loop, and is joined just before the one collective
-  std::mutex nccl_mu;
-  bool nccl_started = false;
-  std::atomic<int> workers_uploaded(0);
-  auto nccl_start = [&] {
-    std::lock_guard<std::mutex> lock(nccl_mu);
-    if (!use_nccl || nccl_started) return;
-    nccl_started = true;
-    nccl_init_thread = std::thread([&] {
-      const NcclApi& nc = nccl_api();
-      const double ti = now_s();
-      int r = nc.CommInitAll(comms.data(), ngpu, devs.data());
-      if (r != 0) {
-        nccl_init_rc = MPQC_T_ERR_NCCL;
-        nccl_init_msg = nc.GetErrorString ? nc.GetErrorString(r) : "ncclCommInitAll failed";
-      }
-      nccl_init_seconds = now_s() - ti;
-    });
-  };
-  std::mutex nccl_join_mu;
-  auto nccl_join = [&] {              // any worker may arrive first; start if nobody did, join exactly once
-    nccl_start();
-    std::lock_guard<std::mutex> lock(nccl_join_mu);
-    if (nccl_init_thread.joinable()) nccl_init_thread.join();
-  };
+  std::vector<mpqc_t_stats> gstats(nlocal);
+  std::vector<int> rcs(nlocal, MPQC_T_OK);
+  std::vector<std::string> msgs(nlocal);
+  std::vector<double> reduced;                       // unit energies after the all-reduce (written by local worker 0)
+  if (exchange) reduced.assign((size_t)count, 0.0);
 
   auto worker = [&](int g) {
     mpqc_t_stats& gs = gstats[g];
     memset(&gs, 0, sizeof(gs));
+    const CommView& cv = views[g];
+    const int wrank = comm ? cv.rank : g;
     mpqc_t_handle* h = nullptr;
     const double tw0 = now_s();
-    int rc = mpqc_t_create(&h, p->o, p->v, devs[g]);
+    int rc = mpqc_t_create(&h, prob_o, prob_v, devs[g]);
+    cudaStream_t cst = nullptr;                       // stream of this worker's collectives
+    if (exchange) {
+      cudaSetDevice(devs[g]);
+      if (h) cst = h->stream;
+      else if (cudaStreamCreateWithFlags(&cst, cudaStreamNonBlocking) != cudaSuccess) cst = nullptr;
+      // agreement #1: every rank holds its operand memory, or nobody starts the replicated upload
+      const int nfail = cst ? count_failed_ranks(cv, rc, cst) : -1;
+      if (rc == MPQC_T_OK && nfail != 0)
+        rc = fail(nfail < 0 ? MPQC_T_ERR_NCCL : MPQC_T_ERR_INTERNAL,
+                  "another rank of the (T) communicator failed to set up its device", __FILE__, __LINE__);
+    }
     const double tw1 = now_s();
-    if (rc == MPQC_T_OK) rc = upload(h, &gs);
+    if (rc == MPQC_T_OK) rc = upload(h, cv, &gs);
     const double tw2 = now_s();
-    if (workers_uploaded.fetch_add(1) + 1 == ngpu) nccl_start();
-    std::vector<int64_t> done_idx;     // slots of unit_e this worker produced (for its NCCL contribution)
+    std::vector<int64_t> done_idx;     // job positions this worker produced
     if (rc == MPQC_T_OK) {
-      // static part
-      std::vector<int64_t> mine;
-      for (int64_t u = g; u < static_n; u += ngpu) mine.push_back(u);
-      std::vector<int64_t> idx(mine.size());
+      // static share
+      std::vector<int64_t> mine, idx;
+      for (int64_t q = wrank; q < static_n; q += W) mine.push_back(q);
+      idx.resize(mine.size());
       std::vector<double> e(mine.size());
-      for (size_t q = 0; q < mine.size(); ++q) idx[q] = units[mine[q]];
-      rc = run_units(h, all, idx.data(), (int64_t)idx.size(), opt.batch, e.data(), &gs, profile);
+      for (size_t q = 0; q < mine.size(); ++q) idx[q] = opt.unit_first + mine[q] * stride;
+      rc = run_units(h, ux, idx.data(), (int64_t)idx.size(), opt.batch, e.data(), &gs, profile);
       if (rc == MPQC_T_OK)
         for (size_t q = 0; q < mine.size(); ++q) {
-          unit_e[mine[q]] = e[q];
+          unit_e[(size_t)mine[q]] = e[q];
           done_idx.push_back(mine[q]);
         }
-      // work-stealing tail
-      int64_t chunk = opt.steal_chunk > 0 ? opt.steal_chunk : std::max<int64_t>(1, auto_batch(h)) * 4;
-      while (rc == MPQC_T_OK) {
-        int64_t s = tail_next.fetch_add(chunk);
-        if (s >= count) break;
-        int64_t n = std::min(chunk, count - s);
+      // work-stealing tail (only when all workers share this process)
+      const int64_t chunk = opt.steal_chunk > 0 ? opt.steal_chunk : std::max<int64_t>(1, auto_batch(h)) * 4;
+      while (rc == MPQC_T_OK && static_n < count) {
+        const int64_t s0 = tail_next.fetch_add(chunk);
+        if (s0 >= count) break;
+        const int64_t n = std::min(chunk, count - s0);
+        std::vector<int64_t> ids((size_t)n);
+        for (int64_t q = 0; q < n; ++q) ids[(size_t)q] = opt.unit_first + (s0 + q) * stride;
         std::vector<double> e2((size_t)n);
-        rc = run_units(h, all, units.data() + s, n, opt.batch, e2.data(), &gs, profile);
+        rc = run_units(h, ux, ids.data(), n, opt.batch, e2.data(), &gs, profile);
         if (rc == MPQC_T_OK)
           for (int64_t q = 0; q < n; ++q) {
-            unit_e[s + q] = e2[q];
-            done_idx.push_back(s + q);
+            unit_e[(size_t)(s0 + q)] = e2[(size_t)q];
+            done_idx.push_back(s0 + q);
           }
       }
     }
-    if (use_nccl) {
-      // every thread must reach the collective, also after a failure (contribute zeros)
-      const NcclApi& nc = nccl_api();
-      nccl_join();
+    if (exchange && cst) {
+      // the path's one arithmetic collective (replaces gop.sum, ccsd_t.h:692).  Every rank reaches it, also after
+      // a local failure (it then contributes zeros and a raised status word).
       cudaSetDevice(devs[g]);
-      double* dbuf = nullptr;
-      cudaStream_t st = nullptr;
-      int r2 = MPQC_T_OK;
-      if (nccl_init_rc != MPQC_T_OK) {
-        r2 = fail(MPQC_T_ERR_NCCL, nccl_init_msg.c_str(), __FILE__, __LINE__);
-      } else if (cudaMalloc(&dbuf, (size_t)count * sizeof(double)) != cudaSuccess || cudaStreamCreate(&st) != cudaSuccess) {
-        r2 = fail(MPQC_T_ERR_OOM, "allocation for the NCCL sum failed", __FILE__, __LINE__);
-      } else {
-        std::vector<double> mine((size_t)count, 0.0);
-        if (rc == MPQC_T_OK)
-          for (int64_t u : done_idx) mine[u] = unit_e[u];   // only the slots this thread wrote itself
-        cudaMemcpyAsync(dbuf, mine.data(), (size_t)count * sizeof(double), cudaMemcpyHostToDevice, st);
-        int r = nc.AllReduce(dbuf, dbuf, (size_t)count, kNcclFloat64, kNcclSum, comms[g], st);
-        if (r != 0) r2 = fail(MPQC_T_ERR_NCCL, nc.GetErrorString ? nc.GetErrorString(r) : "ncclAllReduce failed", __FILE__, __LINE__);
-        if (g == 0 && r2 == MPQC_T_OK)
-          cudaMemcpyAsync(nccl_result.data(), dbuf, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, st);
-        if (cudaStreamSynchronize(st) != cudaSuccess && r2 == MPQC_T_OK)
-          r2 = fail(MPQC_T_ERR_CUDA, "stream sync after ncclAllReduce failed", __FILE__, __LINE__);
+      std::vector<double> mine((size_t)count + 1, 0.0);
+      if (rc == MPQC_T_OK)
+        for (int64_t q : done_idx) mine[(size_t)q] = unit_e[(size_t)q];   // only the slots this worker wrote itself
+      mine[(size_t)count] = rc == MPQC_T_OK ? 0.0 : 1.0;
+      const std::string keep = last_error_string();
+      const int r2 = allreduce_host_vector(cv, mine.data(), mine.size(), cst);
+      if (rc != MPQC_T_OK) last_error_string() = keep;
+      if (rc == MPQC_T_OK) {
+        if (r2 != MPQC_T_OK) rc = r2;
+        else if (mine[(size_t)count] > 0.5)
+          rc = fail(MPQC_T_ERR_INTERNAL, "another rank of the (T) communicator failed during the triples loop", __FILE__, __LINE__);
+        else if (g == 0) std::copy(mine.begin(), mine.begin() + count, reduced.begin());
       }
-      cudaFree(dbuf);
-      if (st) cudaStreamDestroy(st);
-      if (rc == MPQC_T_OK) rc = r2;
+      gs.bytes_h2d += (int64_t)mine.size() * 8;
+      gs.bytes_d2h += (int64_t)mine.size() * 8;
     }
     if (rc != MPQC_T_OK) msgs[g] = last_error_string();
     const double tw3 = now_s();
+    if (!h && cst) cudaStreamDestroy(cst);
     mpqc_t_destroy(h);
     if (opt.verbose >= 2)
-      printf("  [mpqc_t] gpu %d: create %.3f s, upload+relayout %.3f s, triples+sum %.3f s, destroy %.3f s\n", devs[g],
-             tw1 - tw0, tw2 - tw1, tw3 - tw2, now_s() - tw3);
+      printf("  [mpqc_t] rank %d gpu %d: create %.3f s, upload+relayout %.3f s, triples+sum %.3f s, destroy %.3f s\n", wrank,
+             devs[g], tw1 - tw0, tw2 - tw1, tw3 - tw2, now_s() - tw3);
     rcs[g] = rc;
   };
 
-  if (ngpu == 1) {
+  if (nlocal == 1) {
     worker(0);
   } else {
     std::vector<std::thread> th;
-    for (int g = 0; g < ngpu; ++g) th.emplace_back(worker, g);
+    for (int g = 0; g < nlocal; ++g) th.emplace_back(worker, g);
     for (auto& t : th) t.join();   // joined before returning (SURVEY 8b threading contract)
   }
-  if (use_nccl) {
-    const NcclApi& nc = nccl_api();
-    nccl_join();
-    for (int g = 0; g < ngpu; ++g)
-      if (comms[g]) nc.CommDestroy(comms[g]);
-  }
-  for (int g = 0; g < ngpu; ++g)
+  for (int g = 0; g < nlocal; ++g)
     if (rcs[g] != MPQC_T_OK) {
       last_error_string() = msgs[g];
       return rcs[g];
     }
   double e = 0.0;
-  if (use_nccl) {
-    for (int64_t u = 0; u < count; ++u) e += nccl_result[u];   // the NCCL-summed vector, in unit order
-  } else {
-    for (int64_t u = 0; u < count; ++u) e += unit_e[u];
-  }
+  const std::vector<double>& final_e = exchange ? reduced : unit_e;
+  for (int64_t u = 0; u < count; ++u) e += final_e[(size_t)u];   // unit order: bit-identical for any number of GPUs
   *e_t = e;
 
-  for (int g = 0; g < ngpu; ++g) {
+  for (int g = 0; g < nlocal; ++g) {
     stats.seconds_upload = std::max(stats.seconds_upload, gstats[g].seconds_upload);
     stats.seconds_relayout = std::max(stats.seconds_relayout, gstats[g].seconds_relayout);
     stats.seconds_compute = std::max(stats.seconds_compute, gstats[g].seconds_compute);
@@ -1110,10 +1265,8 @@ int energy_impl(const int64_t prob_o, const int64_t prob_v, const UploadFn& uplo
     stats.bytes_h2d += gstats[g].bytes_h2d;
     stats.bytes_d2h += gstats[g].bytes_d2h;
   }
-  stats.ngpu = ngpu;
+  stats.ngpu = nlocal;
   stats.seconds_total = now_s() - t0;
-  if (opt.verbose >= 2)
-    printf("  [mpqc_t] nccl init (background) %.3f s; total %.3f s\n", nccl_init_seconds, stats.seconds_total);
   if (opt.verbose) {
     // same line the reference prints, ccsd_t.h:175
     printf("(T) Energy: %.15g Time: %g S\n", e, stats.seconds_total);
@@ -1137,20 +1290,181 @@ int validate_df_problem(const mpqc_t_df_problem* p) {
 
 extern "C" {
 
-int mpqc_t_energy(const mpqc_t_problem* p, const mpqc_t_options* opt, double* e_t, mpqc_t_stats* stats) {
+static int energy_dense(mpqc_t_comm* c, const mpqc_t_problem* p, const mpqc_t_options* opt, double* e_t, mpqc_t_stats* stats) {
   MPQC_T_CHECK(e_t != nullptr, MPQC_T_ERR_BAD_ARG, "e_t is NULL");
   MPQC_T_TRY(validate_problem(p));
-  const int on_dev = opt ? opt->inputs_on_device : 0;
-  return energy_impl(p->o, p->v, [&](mpqc_t_handle* h, mpqc_t_stats* st) { return mpqc_t_upload(h, p, on_dev, st); },
-                     opt, e_t, stats);
+  const bool on_dev = opt && opt->inputs_on_device;
+  return energy_impl(p->o, p->v,
+                     [&](mpqc_t_handle* h, const CommView& cv, mpqc_t_stats* st) {
+                       MPQC_T_CUDA(cudaSetDevice(h->device));
+                       return upload_impl(h, p, on_dev, cv, st);
+                     },
+                     opt, c, e_t, stats);
+}
+
+static int energy_df(mpqc_t_comm* c, const mpqc_t_df_problem* p, const mpqc_t_options* opt, double* e_t, mpqc_t_stats* stats) {
+  MPQC_T_CHECK(e_t != nullptr, MPQC_T_ERR_BAD_ARG, "e_t is NULL");
+  MPQC_T_TRY(validate_df_problem(p));
+  const bool on_dev = opt && opt->inputs_on_device;
+  return energy_impl(p->o, p->v,
+                     [&](mpqc_t_handle* h, const CommView& cv, mpqc_t_stats* st) {
+                       MPQC_T_CUDA(cudaSetDevice(h->device));
+                       return upload_df_impl(h, p, on_dev, cv, st);
+                     },
+                     opt, c, e_t, stats);
+}
+
+int mpqc_t_energy(const mpqc_t_problem* p, const mpqc_t_options* opt, double* e_t, mpqc_t_stats* stats) {
+  return energy_dense(nullptr, p, opt, e_t, stats);
 }
 
 int mpqc_t_energy_df(const mpqc_t_df_problem* p, const mpqc_t_options* opt, double* e_t, mpqc_t_stats* stats) {
-  MPQC_T_CHECK(e_t != nullptr, MPQC_T_ERR_BAD_ARG, "e_t is NULL");
-  MPQC_T_TRY(validate_df_problem(p));
-  const int on_dev = opt ? opt->inputs_on_device : 0;
-  return energy_impl(p->o, p->v, [&](mpqc_t_handle* h, mpqc_t_stats* st) { return mpqc_t_upload_df(h, p, on_dev, st); },
-                     opt, e_t, stats);
+  return energy_df(nullptr, p, opt, e_t, stats);
+}
+
+int mpqc_t_energy_comm(mpqc_t_comm* c, const mpqc_t_problem* p, const mpqc_t_options* opt, double* e_t, mpqc_t_stats* stats) {
+  MPQC_T_CHECK(c != nullptr, MPQC_T_ERR_BAD_ARG, "communicator is NULL");
+  return energy_dense(c, p, opt, e_t, stats);
+}
+
+int mpqc_t_energy_df_comm(mpqc_t_comm* c, const mpqc_t_df_problem* p, const mpqc_t_options* opt, double* e_t,
+                          mpqc_t_stats* stats) {
+  MPQC_T_CHECK(c != nullptr, MPQC_T_ERR_BAD_ARG, "communicator is NULL");
+  return energy_df(c, p, opt, e_t, stats);
+}
+
+// ---- communicator -------------------------------------------------------------------------------------------
+int mpqc_t_comm_unique_id(mpqc_t_unique_id* id) {
+  MPQC_T_CHECK(id != nullptr, MPQC_T_ERR_BAD_ARG, "id is NULL");
+  const NcclApi& nc = nccl_api();
+  MPQC_T_CHECK(nc.ok, MPQC_T_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  MPQC_T_NCCL(nc.GetUniqueId(reinterpret_cast<NcclUniqueId*>(id)));
+  return MPQC_T_OK;
+}
+
+static int comm_member_init(CommMember& m) {
+  MPQC_T_CUDA(cudaSetDevice(m.device));
+  MPQC_T_CUDA(cudaMalloc(&m.scratch, kCommScratchDoubles * sizeof(double)));
+  return MPQC_T_OK;
+}
+
+int mpqc_t_comm_create_rank(mpqc_t_comm** out, int32_t nranks, int32_t rank, const mpqc_t_unique_id* id, int32_t device) {
+  MPQC_T_CHECK(out != nullptr, MPQC_T_ERR_BAD_ARG, "communicator pointer is NULL");
+  *out = nullptr;
+  MPQC_T_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, MPQC_T_ERR_BAD_ARG, "need 0 <= rank < nranks");
+  MPQC_T_CHECK(id != nullptr || nranks == 1, MPQC_T_ERR_BAD_ARG, "unique id is NULL");
+  const int ndev = mpqc_t_device_count();
+  MPQC_T_CHECK(ndev > 0, MPQC_T_ERR_NO_DEVICE, "no CUDA device visible; the (T) path has no CPU fallback");
+  MPQC_T_CHECK(device >= 0 && device < ndev, MPQC_T_ERR_BAD_ARG, "device ordinal out of range");
+  mpqc_t_comm* c = new (std::nothrow) mpqc_t_comm();
+  MPQC_T_CHECK(c != nullptr, MPQC_T_ERR_OOM, "host allocation failed");
+  c->nranks = nranks;
+  c->local = nranks == 1;
+  c->members.resize(1);
+  c->members[0].rank = rank;
+  c->members[0].device = device;
+  int rc = comm_member_init(c->members[0]);
+  if (rc == MPQC_T_OK && nranks > 1) {
+    const NcclApi& nc = nccl_api();
+    if (!nc.ok) rc = fail(MPQC_T_ERR_NCCL, "libnccl.so.2 could not be loaded", __FILE__, __LINE__);
+    else {
+      NcclUniqueId uid;
+      memcpy(&uid, id, sizeof(uid));
+      rc = nccl_status(nc.CommInitRank(&c->members[0].comm, nranks, uid, rank), "ncclCommInitRank", __FILE__, __LINE__);
+    }
+  }
+  if (rc != MPQC_T_OK) {
+    const std::string keep = last_error_string();
+    mpqc_t_comm_destroy(c);
+    last_error_string() = keep;
+    return rc;
+  }
+  *out = c;
+  return MPQC_T_OK;
+}
+
+int mpqc_t_comm_create_local(mpqc_t_comm** out, int32_t ngpu, const int32_t* device_ids) {
+  MPQC_T_CHECK(out != nullptr, MPQC_T_ERR_BAD_ARG, "communicator pointer is NULL");
+  *out = nullptr;
+  MPQC_T_CHECK(ngpu >= 1, MPQC_T_ERR_BAD_ARG, "ngpu must be >= 1");
+  const int ndev = mpqc_t_device_count();
+  MPQC_T_CHECK(ndev > 0, MPQC_T_ERR_NO_DEVICE, "no CUDA device visible; the (T) path has no CPU fallback");
+  std::vector<int> devs(ngpu);
+  for (int g = 0; g < ngpu; ++g) {
+    devs[g] = device_ids ? device_ids[g] : g;
+    MPQC_T_CHECK(devs[g] >= 0 && devs[g] < ndev, MPQC_T_ERR_BAD_ARG, "device ordinal out of range");
+  }
+  mpqc_t_comm* c = new (std::nothrow) mpqc_t_comm();
+  MPQC_T_CHECK(c != nullptr, MPQC_T_ERR_OOM, "host allocation failed");
+  c->nranks = ngpu;
+  c->local = true;
+  c->members.resize(ngpu);
+  // CUDA contexts are created here, one thread per device, so that the serial seconds of context creation in a
+  // process that drives 8 GPUs are paid once and in parallel, outside the (T) call
+  std::vector<int> rcs(ngpu, MPQC_T_OK);
+  std::vector<std::string> msgs(ngpu);
+  {
+    std::vector<std::thread> th;
+    for (int g = 0; g < ngpu; ++g)
+      th.emplace_back([&, g] {
+        c->members[g].rank = g;
+        c->members[g].device = devs[g];
+        rcs[g] = comm_member_init(c->members[g]);
+        if (rcs[g] != MPQC_T_OK) msgs[g] = last_error_string();
+      });
+    for (auto& t : th) t.join();
+  }
+  int rc = MPQC_T_OK;
+  for (int g = 0; g < ngpu && rc == MPQC_T_OK; ++g)
+    if (rcs[g] != MPQC_T_OK) {
+      last_error_string() = msgs[g];
+      rc = rcs[g];
+    }
+  if (rc == MPQC_T_OK && ngpu > 1) {
+    const NcclApi& nc = nccl_api();
+    if (!nc.ok) rc = fail(MPQC_T_ERR_NCCL, "libnccl.so.2 could not be loaded", __FILE__, __LINE__);
+    else {
+      std::vector<NcclApi::comm_t> comms(ngpu, nullptr);
+      rc = nccl_status(nc.CommInitAll(comms.data(), ngpu, devs.data()), "ncclCommInitAll", __FILE__, __LINE__);
+      for (int g = 0; g < ngpu; ++g) c->members[g].comm = comms[g];
+    }
+  }
+  if (rc != MPQC_T_OK) {
+    const std::string keep = last_error_string();
+    mpqc_t_comm_destroy(c);
+    last_error_string() = keep;
+    return rc;
+  }
+  *out = c;
+  return MPQC_T_OK;
+}
+
+int mpqc_t_comm_destroy(mpqc_t_comm* c) {
+  if (!c) return MPQC_T_OK;
+  const NcclApi& nc = nccl_api();
+  for (CommMember& m : c->members) {
+    cudaSetDevice(m.device);
+    if (m.comm && nc.ok) nc.CommDestroy(m.comm);
+    cudaFree(m.scratch);
+  }
+  cudaGetLastError();
+  delete c;
+  return MPQC_T_OK;
+}
+
+int mpqc_t_comm_size(const mpqc_t_comm* c) { return c ? c->nranks : 0; }
+
+int mpqc_t_host_alloc(void** ptr, size_t bytes) {
+  MPQC_T_CHECK(ptr != nullptr, MPQC_T_ERR_BAD_ARG, "pointer is NULL");
+  *ptr = nullptr;
+  MPQC_T_CHECK(mpqc_t_device_count() > 0, MPQC_T_ERR_NO_DEVICE, "no CUDA device visible; the (T) path has no CPU fallback");
+  MPQC_T_CUDA(cudaHostAlloc(ptr, std::max<size_t>(bytes, 1), cudaHostAllocPortable));
+  return MPQC_T_OK;
+}
+
+int mpqc_t_host_free(void* ptr) {
+  if (ptr) MPQC_T_CUDA(cudaFreeHost(ptr));
+  return MPQC_T_OK;
 }
 
 int mpqc_t_upload_df(mpqc_t_handle* h, const mpqc_t_df_problem* p, int32_t on_device, mpqc_t_stats* stats) {
@@ -1158,7 +1472,7 @@ int mpqc_t_upload_df(mpqc_t_handle* h, const mpqc_t_df_problem* p, int32_t on_de
   MPQC_T_TRY(validate_df_problem(p));
   MPQC_T_CHECK(p->o == h->o && p->v == h->v, MPQC_T_ERR_BAD_ARG, "problem dimensions differ from the handle's");
   MPQC_T_CUDA(cudaSetDevice(h->device));
-  return upload_df_impl(h, p, on_device != 0, stats);
+  return upload_df_impl(h, p, on_device != 0, CommView(), stats);
 }
 
 int mpqc_t_microbench(int32_t device, int32_t which, double* tflops) {

@@ -220,4 +220,23 @@ t_energy_finish_kernel(const double* __restrict__ partial, int ntt, const int* _
   }
 }
 
+// Decomposition of the same energy over virtual-block triples (validation aid, mpqc_t_run_vblocks):
+//   vblock_e[tt] += sum_b weight(i,j,k)_b * partial[b][tt]
+// tt enumerates 8-wide virtual tiles TA >= TB >= TC exactly like global_iter - 1 of the reference's coarse loop with
+// block size 8 (ccsd_t.h:443-480), so vblock_e[tt] equals the energy that loop iteration adds (ccsd_t.h:619-638).
+// One thread per tt walks the batch in order: deterministic.
+__global__ void __launch_bounds__(256)
+t_energy_vblock_kernel(const double* __restrict__ partial, int ntt, int nbatch, const int* __restrict__ triples,
+                       double* __restrict__ vblock_e) {
+  const int tt = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tt >= ntt) return;
+  double s = 0.0;
+  for (int b = 0; b < nbatch; ++b) {
+    const int i = triples[3 * b], j = triples[3 * b + 1], k = triples[3 * b + 2];
+    const double wgt = (i == j && j == k) ? 0.0 : ((i == j || j == k || i == k) ? 1.0 : 2.0);
+    s += wgt * partial[(int64_t)b * ntt + tt];
+  }
+  vblock_e[tt] += s;
+}
+
 }  // namespace mpqc_t

@@ -222,7 +222,7 @@ __device__ __forceinline__ void producer_loop(const GemmParams& P, const CUtenso
         for (int term = 0; term < 2; ++term) {
           for (int kb = 0; kb < P.kblocks; kb += kSub) {
             const int nsub = (P.kblocks - kb) < kSub ? (P.kblocks - kb) : kSub;
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)nsub * (a_bytes + b_bytes));
             for (int sub = 0; sub < nsub; ++sub) {
               uint8_t* sa = smem + stage * kStageBytes + sub * kSubBytes;
@@ -241,6 +241,12 @@ __device__ __forceinline__ void producer_loop(const GemmParams& P, const CUtenso
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
+      }
+      // drain: stay until the consumers have released every slot of the last fills, so that this (bounded) lane
+      // outlives all their (unbounded) waits -- a stalled pipeline then ends in a trap, not in a hang
+      for (int s = 0; s < kStages; ++s) {
+        mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
 }
 

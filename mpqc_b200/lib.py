@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmpqc_t_cuda.so")
+# MPQC_T_LIB selects an experiment build of the same library (A/B runs, build.py --out=...); never a fallback
+LIB_PATH = os.environ.get("MPQC_T_LIB") or os.path.join(_HERE, "libmpqc_t_cuda.so")
 
 OK, ERR_BAD_ARG, ERR_NO_DEVICE, ERR_OOM, ERR_CUDA, ERR_NCCL, ERR_INTERNAL = range(7)
 
@@ -54,6 +55,10 @@ class Stats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
 
 
+class UniqueId(C.Structure):
+    _fields_ = [("internal", C.c_char * 128)]
+
+
 class MpqcTError(RuntimeError):
     def __init__(self, status: int, what: str, detail: str):
         super().__init__(f"{what}: status {status} ({detail})")
@@ -63,6 +68,8 @@ class MpqcTError(RuntimeError):
 #: every symbol include/mpqc_t.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "mpqc_t_energy", "mpqc_t_energy_df", "mpqc_t_create", "mpqc_t_upload", "mpqc_t_upload_df", "mpqc_t_run", "mpqc_t_debug_w", "mpqc_t_stream",
+    "mpqc_t_comm_unique_id", "mpqc_t_comm_create_rank", "mpqc_t_comm_create_local", "mpqc_t_comm_size", "mpqc_t_comm_destroy",
+    "mpqc_t_energy_comm", "mpqc_t_energy_df_comm", "mpqc_t_host_alloc", "mpqc_t_host_free", "mpqc_t_run_vblocks", "mpqc_t_run_comm",
     "mpqc_t_destroy", "mpqc_t_triple_count", "mpqc_t_triple_of_unit", "mpqc_t_flops", "mpqc_t_unit_flops",
     "mpqc_t_device_count", "mpqc_t_plan", "mpqc_t_version", "mpqc_t_strerror", "mpqc_t_last_error", "mpqc_t_microbench",
 ]
@@ -94,6 +101,30 @@ def load() -> C.CDLL:
     lib.mpqc_t_run.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int32, c_double_p, c_double_p,
                                C.POINTER(Stats)]
     lib.mpqc_t_run.restype = C.c_int
+    lib.mpqc_t_run_vblocks.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int32, c_double_p, c_double_p, c_double_p,
+                                       C.POINTER(Stats)]
+    lib.mpqc_t_run_vblocks.restype = C.c_int
+    lib.mpqc_t_run_comm.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int32, c_double_p, c_double_p,
+                                    C.POINTER(Stats)]
+    lib.mpqc_t_run_comm.restype = C.c_int
+    lib.mpqc_t_comm_unique_id.argtypes = [C.POINTER(UniqueId)]
+    lib.mpqc_t_comm_unique_id.restype = C.c_int
+    lib.mpqc_t_comm_create_rank.argtypes = [C.POINTER(vp), C.c_int32, C.c_int32, C.POINTER(UniqueId), C.c_int32]
+    lib.mpqc_t_comm_create_rank.restype = C.c_int
+    lib.mpqc_t_comm_create_local.argtypes = [C.POINTER(vp), C.c_int32, C.POINTER(C.c_int32)]
+    lib.mpqc_t_comm_create_local.restype = C.c_int
+    lib.mpqc_t_comm_size.argtypes = [vp]
+    lib.mpqc_t_comm_size.restype = C.c_int
+    lib.mpqc_t_comm_destroy.argtypes = [vp]
+    lib.mpqc_t_comm_destroy.restype = C.c_int
+    lib.mpqc_t_energy_comm.argtypes = [vp, C.POINTER(Problem), C.POINTER(Options), c_double_p, C.POINTER(Stats)]
+    lib.mpqc_t_energy_comm.restype = C.c_int
+    lib.mpqc_t_energy_df_comm.argtypes = [vp, C.POINTER(DfProblem), C.POINTER(Options), c_double_p, C.POINTER(Stats)]
+    lib.mpqc_t_energy_df_comm.restype = C.c_int
+    lib.mpqc_t_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    lib.mpqc_t_host_alloc.restype = C.c_int
+    lib.mpqc_t_host_free.argtypes = [vp]
+    lib.mpqc_t_host_free.restype = C.c_int
     lib.mpqc_t_debug_w.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, c_double_p]
     lib.mpqc_t_debug_w.restype = C.c_int
     lib.mpqc_t_stream.argtypes = [vp]

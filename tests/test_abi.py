@@ -37,6 +37,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(L.Problem) == 2 * 8 + 7 * 8
     assert C.sizeof(L.Options) == 4 + 4 + 8 + 4 + 4 + 3 * 8 + 3 * 4 + 5 * 4
     assert C.sizeof(L.Stats) == 8 * 8 + 4 * 8 + 8 * 4
+    assert C.sizeof(L.UniqueId) == 128
 
 
 def test_version_and_strerror(lib):
@@ -54,6 +55,25 @@ def test_unit_enumeration_matches_oracle(lib, o):
         assert lib.mpqc_t_triple_of_unit(o, u, C.byref(i), C.byref(j), C.byref(k)) == L.OK
         assert (i.value, j.value, k.value) == t
     assert lib.mpqc_t_triple_of_unit(o, len(tr), C.byref(i), C.byref(j), C.byref(k)) == L.ERR_BAD_ARG
+
+
+def test_unit_enumeration_is_arithmetic_at_the_size_limit(lib):
+    # units are decoded in closed form (no O(o^3) list): spot-check group boundaries at the largest accepted o
+    o = 4096
+    n = lib.mpqc_t_triple_count(o)
+    assert n == o * (o + 1) * (o + 2) // 6 - o
+    i, j, k = C.c_int32(), C.c_int32(), C.c_int32()
+
+    def tr(u):
+        assert lib.mpqc_t_triple_of_unit(o, u, C.byref(i), C.byref(j), C.byref(k)) == L.OK
+        return (i.value, j.value, k.value)
+    assert tr(0) == (1, 0, 0) and tr(1) == (1, 1, 0) and tr(2) == (2, 0, 0)
+    assert tr(n - 1) == (o - 1, o - 1, o - 2) and tr(n - 2) == (o - 1, o - 1, o - 3)
+    for a in (2, 63, 1000, 4095):
+        first = a * (a + 1) * (a + 2) // 6 - a          # units before leading index a
+        assert tr(first) == (a, 0, 0) and tr(first - 1) == (a - 1, a - 1, a - 2)
+        b = a // 2
+        assert tr(first + b * (b + 1) // 2 + b) == (a, b, b) and tr(first + b * (b + 1) // 2 + b + 1) == (a, b + 1, 0)
 
 
 def test_flop_model(lib):

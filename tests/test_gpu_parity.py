@@ -153,6 +153,110 @@ def test_w_intermediate_matches_oracle(lib):
         h.close()
 
 
+def test_virtual_block_decomposition_matches_coarse_loop(lib):
+    # mpqc_t_run_vblocks splits the SAME energy over 8-wide virtual block triples a >= b >= c; every entry must equal
+    # the energy the reference's coarse loop adds in that iteration (global_iter - 1, ccsd_t.h:443-480, :619-638),
+    # including the diagonal blocks that go through CCSD_T_ReduceSymm and the ragged last block
+    o, v = 5, 21
+    p = make_problem(o, v, seed=88)
+    h = Handle(lib, p)
+    ntt = 3 * 4 * 5 // 6
+    vb = np.zeros(ntt)
+    e, st = C.c_double(), L.Stats()
+    L.check(lib.mpqc_t_run_vblocks(h.h, 0, 1, -1, 0, C.byref(e), None, vb.ctypes.data_as(L.c_double_p), C.byref(st)),
+            "run_vblocks")
+    h.close()
+    e_ref, parts = oc.coarse(*_args(p), vir_block=8, return_parts=True)
+    assert [g for g, _ in parts] == list(range(1, ntt + 1))
+    np.testing.assert_allclose(vb, [x for _, x in parts], atol=TOL)
+    assert abs(vb.sum() - e.value) < 1e-12 and abs(e.value - e_ref) < TOL
+
+
+def test_uracil_dimer_whole_job_vs_sampled_coarse_iterations(lib):
+    # WHOLE-JOB E(T) at the uracil-dimer shape (o=42, v=198, all 13 202 units, BASELINE.json configs[2]) checked
+    # against the reference's own algorithm: the virtual-block decomposition of the GPU result must reproduce sampled
+    # iterations of the coarse loop (strictly ordered, two-equal, all-equal and ragged-edge blocks), each of which
+    # sums over ALL occupied triples -- so every unit of the job is covered by every sampled comparison.
+    o, v = 42, 198
+    pd = make_problem_torch(o, v, "cuda", seed=12)
+    h = Handle(lib, pd, on_device=True)
+    nb = (v + 7) // 8
+    ntt = nb * (nb + 1) * (nb + 2) // 6
+    vb = np.zeros(ntt)
+    e, st = C.c_double(), L.Stats()
+    L.check(lib.mpqc_t_run_vblocks(h.h, 0, 1, -1, 0, C.byref(e), None, vb.ctypes.data_as(L.c_double_p), C.byref(st)),
+            "run_vblocks")
+    h.close()
+    assert st.units == lib.mpqc_t_triple_count(o) == 42 * 43 * 44 // 6 - 42
+    assert abs(vb.sum() - e.value) < 1e-10
+
+    def it(a, b, c):   # global_iter of block triple a >= b >= c
+        return a * (a + 1) * (a + 2) // 6 + b * (b + 1) // 2 + c + 1
+    want = {it(7, 4, 2), it(nb - 1, 11, 3), it(9, 9, 5), it(12, 6, 6), it(3, 3, 3), it(nb - 1, nb - 1, nb - 1), it(1, 0, 0)}
+    ph = {k: (a.cpu().numpy() if torch.is_tensor(a) else a) for k, a in pd.items()}
+    _, parts = oc.coarse(*_args(ph), vir_block=8, block_filter=want, return_parts=True)
+    assert {g for g, _ in parts} == want
+    for g, e_block in parts:
+        assert abs(vb[g - 1] - e_block) < TOL, (g, vb[g - 1], e_block)
+
+
+def test_rank_mode_communicator_of_one(lib):
+    # mpqc_t_energy_comm through a one-rank communicator must be the plain call (no NCCL exchange involved)
+    p = make_problem(6, 22, seed=19)
+    e0, st0 = _energy_oneshot(lib, p)
+    comm = C.c_void_p()
+    L.check(lib.mpqc_t_comm_create_rank(C.byref(comm), 1, 0, None, 0), "comm_create_rank")
+    try:
+        assert lib.mpqc_t_comm_size(comm) == 1
+        prob, opt = _cprob(p), L.Options()
+        opt.unit_count = -1
+        e, st = C.c_double(), L.Stats()
+        L.check(lib.mpqc_t_energy_comm(comm, C.byref(prob), C.byref(opt), C.byref(e), C.byref(st)), "energy_comm")
+        assert e.value == e0 and st.units == st0.units
+        # a sub-job: units 3, 5, 7, ... (10 of them)
+        opt.unit_first, opt.unit_stride, opt.unit_count = 3, 2, 10
+        L.check(lib.mpqc_t_energy_comm(comm, C.byref(prob), C.byref(opt), C.byref(e), C.byref(st)), "energy_comm")
+        h = Handle(lib, p)
+        e_sub, _, _ = h.run(first=3, stride=2, count=10)
+        h.close()
+        assert e.value == e_sub and st.units == 10
+    finally:
+        lib.mpqc_t_comm_destroy(comm)
+
+
+@pytest.mark.parametrize("df", [0, 1])
+def test_local_communicator_replicates_inputs_over_nvlink(lib, df):
+    # one process, several GPUs, persistent communicator: each GPU uploads 1/N of every host tensor, ncclAllGather
+    # completes them, ncclAllReduce sums the unit energies -- bit-identical to the single-GPU result
+    ndev = lib.mpqc_t_device_count()
+    if ndev < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = min(ndev, 4)
+    p = make_problem(9, 41, seed=17)
+    e1, st1 = _energy_oneshot(lib, p)
+    comm = C.c_void_p()
+    L.check(lib.mpqc_t_comm_create_local(C.byref(comm), n, None), "comm_create_local")
+    try:
+        opt = L.Options()
+        opt.unit_count, opt.steal_chunk = -1, 5
+        e, st = C.c_double(), L.Stats()
+        if df:
+            dfp = L.make_df_problem(9, 41, p["naux"], p["eps_occ"], p["eps_vir"], p["t1"], p["t2"], p["x_ab"], p["x_ij"], p["x_ai"])
+            L.check(lib.mpqc_t_energy_df_comm(comm, C.byref(dfp), C.byref(opt), C.byref(e), C.byref(st)), "energy_df_comm")
+            assert abs(e.value - e1) < 1e-12
+        else:
+            prob = _cprob(p)
+            for _ in range(2):     # the communicator is reusable
+                L.check(lib.mpqc_t_energy_comm(comm, C.byref(prob), C.byref(opt), C.byref(e), C.byref(st)), "energy_comm")
+                assert e.value == e1
+            # every host tensor crossed PCIe once in total (plus the small per-rank extras), not once per GPU
+            dense_bytes = 8 * sum(p[k].size for k in ("t2", "g_abij", "g_aijk", "g_abci"))
+            assert st.bytes_h2d < 1.2 * dense_bytes + n * (1 << 16) + 24 * st.units * n
+        assert st.ngpu == n and st.units == st1.units
+    finally:
+        lib.mpqc_t_comm_destroy(comm)
+
+
 def test_sharding_and_batching_are_bitwise_consistent(lib):
     # any unit sharding / batch size gives bit-identical per-unit energies, so 1/2/4/8-GPU sums agree
     p = make_problem(6, 27, seed=9)

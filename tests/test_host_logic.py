@@ -81,7 +81,13 @@ def _rank_main(rank, world, port, o, v, q):
     p = make_problem(o, v)
     args = (p["t1"], p["t2"], p["g_abij"], p["g_aijk"], p["g_abci"], p["eps_occ"], p["eps_vir"])
     # the shard this rank's CCSD_T would hand to mpqc_t_energy: unit_first=rank, unit_stride=world
-    w = CCSD_T({"rank": rank, "world_size": world})
+    def reduce(x):                                      # replaces gop.sum (ccsd_t.h:692); NCCL on the GPU box
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t[0])
+    w = CCSD_T({"rank": rank, "world_size": world}, reduce=reduce)
+    with pytest.raises(InputError):                     # a sharded run without a reducer never stores a partial energy
+        CCSD_T({"rank": rank, "world_size": world}, ccsd=object()).compute_ccsd_t()
     units = oc.ijk_triple_list(o)[w.rank_::w.world_size_]
     partial = oc.ijk_driven(*args, triples=units)       # stand-in for the device result of that shard
     t = torch.tensor([partial], dtype=torch.float64)
@@ -126,18 +132,6 @@ def test_dump_roundtrip_and_h2o_fixture(tmp_path):
         f.write(b"XXXX")
     with pytest.raises(InputError):
         dump.load_problem(path)
-
-
-def test_adapter_header_compiles_against_mocks():
-    # integration/ccsd_t_gpu.h cannot be built against real MPQC here (TiledArray/MADNESS/Libint absent); this is a
-    # C++14 syntax/type check against hand-written mocks of the small interface it touches (tests/mock_mpqc/)
-    import subprocess
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    mock = os.path.join(root, "tests", "mock_mpqc")
-    res = subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-Wall", "-Werror", "-I", mock, "-I",
-                          os.path.join(root, "integration"), "-I", os.path.join(root, "include"),
-                          os.path.join(mock, "check_adapter.cpp")], capture_output=True, text=True)
-    assert res.returncode == 0, res.stderr
 
 
 def test_bench_reference_arm_json_contract():

@@ -1,0 +1,124 @@
+"""The MPQC-side change is an IN-CLASS patch of the reference's own ccsd_t.h (integration/mpqc_ccsd_t_gpu.patch +
+integration/ccsd_t_gpu_impl.h), because the integral getters and triples_energy_ are private members of CCSD_T and
+CCSD(T)F12 calls the non-virtual compute_ccsd_t() of its base.  These CPU tests run where /root/reference exists (this
+container; not the GPU box) and prove, against the REAL header:
+
+  * the unified diff applies cleanly (and reverses cleanly) to the reference tree;
+  * the patched real ccsd_t.h + ccsd_t_gpu_impl.h type-check (g++ -std=c++14 -Wall -Werror) with mocks of TiledArray,
+    MADNESS, Eigen and ccsd.h ONLY -- the CCSD_T class, its access specifiers and the exception classes are the
+    reference's own files;
+  * the subclass route (round 1's adapter) cannot compile against the real header -- the reason for the in-class route;
+  * every CCSD base-class member the GPU code touches is public or protected in the real ccsd.h;
+  * the second caller (CCSD_T_F12) really calls the base's compute_ccsd_t().
+"""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+CC = "src/mpqc/chemistry/qc/lcao/cc"
+PATCH = os.path.join(ROOT, "integration", "mpqc_ccsd_t_gpu.patch")
+MOCK = os.path.join(ROOT, "tests", "mock_mpqc")
+
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF, CC, "ccsd_t.h")),
+                                reason="needs the reference tree (not present on the GPU box)")
+
+
+def _tree(tmp_path, apply=True):
+    dst = tmp_path / "tree"
+    os.makedirs(dst / CC)
+    for f in ("ccsd_t.h", "CMakeLists.txt"):
+        shutil.copy(os.path.join(REF, CC, f), dst / CC / f)
+    if apply:
+        subprocess.run(["patch", "-p1", "-s", "-i", PATCH], cwd=dst, check=True)
+        shutil.copy(os.path.join(ROOT, "integration", "ccsd_t_gpu_impl.h"), dst / CC / "ccsd_t_gpu_impl.h")
+    return dst
+
+
+def _gxx(tree, source, extra=()):
+    return subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-Wall", "-Werror", "-I", MOCK, "-I", str(tree / "src"),
+                           "-I", os.path.join(ROOT, "include"), "-I", os.path.join(REF, "src"), *extra, str(source)],
+                          capture_output=True, text=True)
+
+
+def test_patch_applies_and_reverses_on_the_reference_tree(tmp_path):
+    tree = _tree(tmp_path, apply=False)
+    dry = subprocess.run(["patch", "-p1", "--dry-run", "-i", PATCH], cwd=tree, capture_output=True, text=True)
+    assert dry.returncode == 0 and "FAILED" not in dry.stdout and "fuzz" not in dry.stdout, dry.stdout + dry.stderr
+    subprocess.run(["patch", "-p1", "-s", "-i", PATCH], cwd=tree, check=True)
+    hdr = open(tree / CC / "ccsd_t.h").read()
+    assert 'approach_ == "gpu"' in hdr and "compute_ccsd_t_gpu()" in hdr and '#include "mpqc_t.h"' in hdr
+    assert 'kv.value<std::string>("approach", "gpu")' in hdr            # the GPU path is the new default
+    for cpu in ("coarse", "fine", "straight", "laplace"):               # the CPU approaches stay callable for A/B runs
+        assert f'approach_ == "{cpu}"' in hdr
+    assert "ccsd_t_gpu_impl.h" in open(tree / CC / "CMakeLists.txt").read()
+    back = subprocess.run(["patch", "-p1", "-R", "--dry-run", "-i", PATCH], cwd=tree, capture_output=True, text=True)
+    assert back.returncode == 0, back.stdout + back.stderr
+
+
+def test_patched_real_header_type_checks(tmp_path):
+    tree = _tree(tmp_path)
+    res = _gxx(tree, os.path.join(MOCK, "check_patched_header.cpp"))
+    assert res.returncode == 0, res.stderr[-4000:]
+    # the mocks do not shadow the class under test or the exception hierarchy: those come from the reference
+    assert not os.path.exists(os.path.join(MOCK, "mpqc", "chemistry", "qc", "lcao", "cc", "ccsd_t.h"))
+    assert not os.path.exists(os.path.join(MOCK, "mpqc", "util", "core", "exception.h"))
+
+
+def test_subclass_route_cannot_reach_the_private_getters(tmp_path):
+    # what round 1's adapter did: derive from CCSD_T and call its getters / write triples_energy_.  Against the real
+    # header this is ill-formed (ccsd_t.h:37 and :199 open private sections), hence the in-class patch.
+    tree = _tree(tmp_path)
+    src = tmp_path / "subclass.cpp"
+    src.write_text('#include "mpqc/chemistry/qc/lcao/cc/ccsd_t.h"\n'
+                   "struct Adapter : mpqc::lcao::CCSD_T<TA::TensorD, TA::SparsePolicy> {\n"
+                   "  explicit Adapter(const mpqc::KeyVal &kv);\n"
+                   "  void f() { auto g = this->get_abij(); (void)g; this->triples_energy_ = 0.0; }\n};\n")
+    res = _gxx(tree, src)
+    assert res.returncode != 0
+    assert res.stderr.count("private within this context") >= 2, res.stderr[-2000:]
+
+
+def _access_of(header_text, class_name, member_regex):
+    """access specifier in effect where `member_regex` is declared inside `class class_name`"""
+    m = re.search(r"\nclass %s\b[^;{]*\{" % class_name, header_text)
+    assert m, class_name
+    access, depth, pos = "private", 1, m.end()
+    for line in header_text[pos:].split("\n"):
+        lab = re.match(r"\s*(public|protected|private):\s*$", line)
+        if lab and depth == 1:
+            access = lab.group(1)
+        if depth == 1 and re.search(member_regex, line):
+            return access
+        depth += line.count("{") - line.count("}")
+        if depth <= 0:
+            break
+    raise AssertionError(f"{member_regex} not found in {class_name}")
+
+
+def test_base_class_members_used_by_the_gpu_code_are_accessible():
+    ccsd = open(os.path.join(REF, CC, "ccsd.h")).read()
+    for member in (r"TArray t1\(\) const", r"TArray t2\(\) const", r"bool is_df\(\) const"):
+        assert _access_of(ccsd, "CCSD", member) == "public", member
+    for member in (r"^\s*orbital_energy\(\) \{", r"const TArray get_Xab\(\)", r"const TArray get_Xij\(\)",
+                   r"const TArray get_Xai\(\)", r"bool verbose_;"):
+        assert _access_of(ccsd, "CCSD", member) == "protected", member
+    # ... and the ones that force the in-class route are private in the real CCSD_T
+    ccsd_t = open(os.path.join(REF, CC, "ccsd_t.h")).read()
+    assert _access_of(ccsd_t, "CCSD_T", r"double triples_energy_;") == "private"
+    assert _access_of(ccsd_t, "CCSD_T", r"^\s*void compute_ccsd_t\(\) \{") == "protected"
+    assert re.search(r"\nprivate:\nstruct ReduceBase", ccsd_t)           # the getters above it sit in the :199 private section
+    assert ccsd_t.index("double compute_ccsd_t_coarse_grain(TArray &t1, TArray &t2) {") < ccsd_t.index("const TArray get_abij() {")
+
+
+def test_second_caller_uses_the_patched_dispatcher():
+    f12 = open(os.path.join(REF, "src/mpqc/chemistry/qc/lcao/f12/ccsd_t_f12.h")).read()
+    assert "CCSD_T<Tile, TA::SparsePolicy>::compute_ccsd_t();" in f12        # f12/ccsd_t_f12.h:59
+    assert "this->triples_energy()" in f12
+    # non-virtual in the reference: an override in a subclass would never be reached from here
+    ccsd_t = open(os.path.join(REF, CC, "ccsd_t.h")).read()
+    assert "virtual void compute_ccsd_t" not in ccsd_t
