@@ -95,7 +95,9 @@ typedef struct mpqc_t_options {
   int32_t steal_chunk;        /* in-process multi-GPU: triples per work-stealing grab; 0 -> auto */
   int32_t use_nccl;           /* mpqc_t_energy with ngpu > 1 and no communicator: 1 = build a communicator for this call
                                  (NVLink input replication + ncclAllReduce sum), 0 = replicated uploads + host sum */
-  int32_t reserved[5];
+  int32_t df_block;           /* density-fitted inputs: 0 = automatic (all operand panels resident when they fit, else a panel
+                                 cache), -1 = resident, b > 0 = panel cache walking occupied blocks of edge b (3 b slots) */
+  int32_t reserved[4];
 } mpqc_t_options;
 
 typedef struct mpqc_t_stats {
@@ -163,7 +165,8 @@ int mpqc_t_host_free(void* ptr);
 int mpqc_t_create(mpqc_t_handle** h, int64_t o, int64_t v, int32_t device);
 /* host (on_device=0) or device (on_device=1) buffers -> occupied-major operand layouts in HBM */
 int mpqc_t_upload(mpqc_t_handle* h, const mpqc_t_problem* p, int32_t on_device, mpqc_t_stats* stats);
-/* density-fitted inputs -> the same device layouts (integrals assembled on the device with cuBLAS DGEMMs) */
+/* density-fitted inputs -> the same device layouts; the integral classes are assembled on the device by the library's
+ * own TMA + DMMA GEMM pipeline (no library GEMM), all panels at once or on demand (mpqc_t_set_df_block) */
 int mpqc_t_upload_df(mpqc_t_handle* h, const mpqc_t_df_problem* p, int32_t on_device, mpqc_t_stats* stats);
 /* process units first, first+stride, ... (count of them; <0 = to the end).  partial_e = weighted sum
  * over those units (summed in unit order, so any sharding gives bit-identical per-unit terms);
@@ -186,6 +189,17 @@ int mpqc_t_run_vblocks(mpqc_t_handle* h, int64_t first, int64_t stride, int64_t 
                        double* partial_e, double* unit_e, double* vblock_e, mpqc_t_stats* stats);
 /* debugging / parity aid: W^{abc}_{ijk} of one occupied triple as a dense [v][v][v] host array */
 int mpqc_t_debug_w(mpqc_t_handle* h, int32_t i, int32_t j, int32_t k, double* w_host);
+/* what the last upload decided for this handle */
+enum {
+  MPQC_T_QUERY_PANEL_SLOTS = 0,   /* operand panels held on the device (o when resident) */
+  MPQC_T_QUERY_PANEL_MODE = 1,    /* 1: panel cache (panels built on demand), 0: all resident */
+  MPQC_T_QUERY_FLAT = 2,          /* 1: flat rows + transposed operand copy, 0: row patches */
+  MPQC_T_QUERY_PANELS_BUILT = 3,  /* operand panels assembled from three-centre factors so far */
+  MPQC_T_QUERY_PANEL_BLOCK = 4    /* occupied block edge of the panel walk */
+};
+int mpqc_t_query(mpqc_t_handle* h, int32_t what, int64_t* value);
+/* density-fitted inputs, split-phase form of mpqc_t_options.df_block: call before mpqc_t_upload_df */
+int mpqc_t_set_df_block(mpqc_t_handle* h, int32_t block);
 /* CUDA stream the handle launches on (cudaStream_t as void*), for event timing by the caller */
 void* mpqc_t_stream(mpqc_t_handle* h);
 int mpqc_t_destroy(mpqc_t_handle* h);
@@ -216,6 +230,16 @@ typedef struct mpqc_t_plan_info {
   double bytes_operands;    /* resident operand bytes (A [+AT], B, GV) */
 } mpqc_t_plan_info;
 int mpqc_t_plan(int64_t o, int64_t v, int32_t flat, mpqc_t_plan_info* out);
+
+/* Host-only: device-memory model of the density-fitted path.  block = 0: every operand panel
+ * resident; block = b > 0: panel cache of 3 b slots -- the v^3 o operand is never resident, panels A_x are built on demand
+ * from the three-centre factors on the library's own TMA + DMMA pipeline while the units are walked occupied-block-wise. */
+typedef struct mpqc_t_df_plan_info {
+  int32_t npanel, block, panel_mode, flat;
+  double bytes_panels, bytes_b, bytes_gv, bytes_t2, bytes_factors, bytes_w_workspace, bytes_total;
+  double build_flop_fraction;   /* FLOPs spent building panels / FLOPs of the triples, whole job */
+} mpqc_t_df_plan_info;
+int mpqc_t_plan_df(int64_t o, int64_t v, int64_t naux, int32_t block, int32_t flat, mpqc_t_df_plan_info* out);
 
 /* FP64 pipe microbenchmarks used to fix the roofline denominator on the box:
  * which = 0: DMMA.8x8x4 issue-bound loop (32 warps/SM), 1: DFMA issue-bound loop, 2: DMMA loop at the W-contraction

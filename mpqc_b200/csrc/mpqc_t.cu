@@ -15,7 +15,6 @@
 #include <thread>
 #include <vector>
 
-#include <cublas_v2.h>
 #include <dlfcn.h>
 
 #include <functional>
@@ -98,38 +97,6 @@ struct EventList {
 };
 
 
-// ---- cuBLAS, bound at run time for the same reasons (plain library DGEMMs of the density-fitted upload only) ----
-struct BlasApi {
-  cublasStatus_t (*Create)(cublasHandle_t*) = nullptr;
-  cublasStatus_t (*Destroy)(cublasHandle_t) = nullptr;
-  cublasStatus_t (*SetStream)(cublasHandle_t, cudaStream_t) = nullptr;
-  cublasStatus_t (*DgemmStridedBatched)(cublasHandle_t, cublasOperation_t, cublasOperation_t, int, int, int,
-                                        const double*, const double*, int, long long, const double*, int, long long,
-                                        const double*, double*, int, long long, int) = nullptr;
-  bool ok = false;
-};
-
-const BlasApi& blas_api() {
-  static BlasApi api;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    const char* names[] = {"libcublas.so.12", "libcublas.so"};
-    void* hnd = nullptr;
-    for (const char* n : names) {
-      hnd = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
-      if (hnd) break;
-    }
-    if (!hnd) return;
-    api.Create = reinterpret_cast<decltype(api.Create)>(dlsym(hnd, "cublasCreate_v2"));
-    api.Destroy = reinterpret_cast<decltype(api.Destroy)>(dlsym(hnd, "cublasDestroy_v2"));
-    api.SetStream = reinterpret_cast<decltype(api.SetStream)>(dlsym(hnd, "cublasSetStream_v2"));
-    api.DgemmStridedBatched =
-        reinterpret_cast<decltype(api.DgemmStridedBatched)>(dlsym(hnd, "cublasDgemmStridedBatched"));
-    api.ok = api.Create && api.Destroy && api.SetStream && api.DgemmStridedBatched;
-  });
-  return api;
-}
-
 }  // namespace
 
 // -------------------------------------------------------------------------------------------------
@@ -155,7 +122,20 @@ struct mpqc_t_handle {
   int64_t units_cap = 0;
   int* triples_dev = nullptr;
   double* unit_e_dev = nullptr;
-  cublasHandle_t blas = nullptr;   // only for the density-fitted upload (plain library DGEMMs)
+  // operand pool.  Resident mode: npanel == o, panel x lives in slot x.  Panel-cache mode (density-fitted inputs
+  // whose A does not fit): npanel < o slots, panels A_x are built on demand from the three-centre factors by the
+  // plain-GEMM mode of the W-contraction kernel and kept under LRU while the units are walked occupied-block-wise.
+  int npanel = 0;
+  bool panel_mode = false;
+  int df_block = 0;                // requested occupied block edge of the panel walk (0: automatic)
+  std::vector<int> slot_of;        // [o]  x -> slot, -1 when not resident
+  std::vector<int> x_of_slot;      // [npanel]
+  std::vector<int64_t> slot_stamp; // [npanel] last use (LRU)
+  int64_t stamp = 0;
+  int* slot_map_dev = nullptr;     // [o] device copy of slot_of, read by the kernel in panel mode
+  double *XaiT = nullptr, *XabT = nullptr, *T2raw = nullptr;   // [o][v][Kx], [v][v][Kx], t2[v][v][o][o] (panel mode)
+  int64_t Kx = 0;                  // padded auxiliary dimension roundup8(naux) (>= 16)
+  int64_t panels_built = 0;
 };
 
 namespace {
@@ -202,15 +182,15 @@ int plan(mpqc_t_handle* h) {
 }
 
 int make_maps(mpqc_t_handle* h) {
-  const uint64_t v = (uint64_t)h->v, o = (uint64_t)h->o, Kp = (uint64_t)h->Kp;
+  const uint64_t v = (uint64_t)h->v, o = (uint64_t)h->o, Kp = (uint64_t)h->Kp, np = (uint64_t)h->npanel;
   if (h->flat) {
-    uint64_t dims[3] = {Kp, v * v, o};
+    uint64_t dims[3] = {Kp, v * v, np};
     uint64_t str[2] = {Kp * 8, v * v * Kp * 8};
     uint32_t box[3] = {(uint32_t)kBK, (uint32_t)kBM, 1};
     MPQC_T_TRY(encode_map(&h->tmA_n, h->A, 3, dims, str, box));
     MPQC_T_TRY(encode_map(&h->tmA_t, h->AT, 3, dims, str, box));
   } else {
-    uint64_t dims[4] = {Kp, v, v, o};
+    uint64_t dims[4] = {Kp, v, v, np};
     uint64_t str[3] = {Kp * 8, v * Kp * 8, v * v * Kp * 8};
     uint32_t box_n[4] = {(uint32_t)kBK, (uint32_t)h->tq, (uint32_t)h->tp, 1};
     uint32_t box_t[4] = {(uint32_t)kBK, (uint32_t)h->tp, (uint32_t)h->tq, 1};
@@ -308,6 +288,11 @@ GemmParams gemm_params(const mpqc_t_handle* h, int nbatch, const int* triples_de
   P.rows_valid = h->flat ? kBM : h->tp * h->tq;
   P.triples = triples_dev;
   P.w = h->W;
+  P.a_slot = h->panel_mode ? h->slot_map_dev : nullptr;
+  P.mode = 0;
+  P.ncols = (int)h->v;
+  P.l_div = P.l_mod = P.r_div = P.r_mod = P.o_div = 1;
+  P.out_s1 = P.out_s2 = P.ldw64 = 0;
   return P;
 }
 
@@ -408,12 +393,59 @@ int stage_in(Staged& s, const double* src, size_t n, bool on_device, const CommV
   return MPQC_T_OK;
 }
 
+// Allocates the operand pool A (and AT in flat mode) with `npanel` panel slots, decides the row mode, plans the tiling
+// and encodes the tensor maps.  npanel == o: every panel resident (slot = x).  `extra_bytes`: what the caller will
+// additionally keep on the device (staged factors ...), for the feasibility check.
+int alloc_operands(mpqc_t_handle* h, int npanel, double extra_bytes) {
+  const int64_t o = h->o, v = h->v;
+  cudaFree(h->A);
+  cudaFree(h->AT);
+  h->A = h->AT = nullptr;
+  free_work(h);
+  size_t free_b = 0, total_b = 0;
+  MPQC_T_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  // "flat" mode keeps a transposed copy AT of the big operand so both GEMM terms read 128 consecutive
+  // flattened (p,q) rows (no row-patch padding).  Use it when 2|A| + the rest leaves >= 25% of free HBM.
+  const double a_bytes = (double)npanel * v * v * h->Kp * 8.0;
+  const double w_one = 3.0 * (double)v * v * (double)roundup(v, 16) * 8.0;
+  const char* env = getenv("MPQC_T_FLAT");
+  h->flat = (2.0 * a_bytes + extra_bytes + 8e9) < 0.75 * (double)free_b ? 1 : 0;
+  if (env) h->flat = atoi(env) != 0;
+  // feasibility: the accepted (o, v) range is far wider than what one device can hold.  Refuse here, with the numbers,
+  // instead of failing inside some later cudaMalloc: operand pool + the W workspace of ONE triple + the caller's extras.
+  const double need = a_bytes * (h->flat ? 2.0 : 1.0) + w_one + extra_bytes;
+  if (need > 0.98 * (double)free_b) {
+    char buf[360];
+    snprintf(buf, sizeof(buf),
+             "problem o=%lld v=%lld needs %.1f GB more device memory (operand panels %.1f GB in %d slots, W workspace "
+             "%.1f GB per triple, staging %.1f GB) but only %.1f GB are free on device %d",
+             (long long)o, (long long)v, need * 1e-9, a_bytes * (h->flat ? 2.0 : 1.0) * 1e-9, npanel, w_one * 1e-9,
+             extra_bytes * 1e-9, (double)free_b * 1e-9, h->device);
+    return fail(MPQC_T_ERR_OOM, buf, __FILE__, __LINE__);
+  }
+  h->npanel = npanel;
+  h->panel_mode = npanel < o;
+  MPQC_T_CUDA(cudaMalloc(&h->A, (size_t)npanel * v * v * h->Kp * sizeof(double)));
+  if (h->flat) MPQC_T_CUDA(cudaMalloc(&h->AT, (size_t)npanel * v * v * h->Kp * sizeof(double)));
+  MPQC_T_TRY(plan(h));
+  MPQC_T_TRY(make_maps(h));
+  h->slot_of.assign((size_t)o, -1);
+  h->x_of_slot.assign((size_t)npanel, -1);
+  h->slot_stamp.assign((size_t)npanel, 0);
+  if (!h->panel_mode)
+    for (int64_t x = 0; x < o; ++x) h->slot_of[(size_t)x] = h->x_of_slot[(size_t)x] = (int)x;
+  return MPQC_T_OK;
+}
+
 int upload_impl(mpqc_t_handle* h, const mpqc_t_problem* p, bool on_device, const CommView& cv, mpqc_t_stats* stats) {
   const int64_t o = h->o, v = h->v, Kp = h->Kp;
   cudaStream_t st = h->stream;
   int64_t launches = 0, h2d = 0;
   const double t0 = now_s();
   double t_copy = 0.0;
+  h->uploaded = false;
+  // dense inputs: all o panels resident; transient staging = t2 + g_abij + g_aijk copies and two <ia|bc> slabs
+  MPQC_T_TRY(alloc_operands(h, (int)o, on_device ? 0.0 : (2.0 * v * v * o * o + (double)v * o * o * o) * 8.0 + 2.2e9));
   // Ordering contract (include/mpqc_t.h): device-resident inputs may have been produced on any stream of the caller;
   // the handle's stream is non-blocking, so wait for the whole device before reading them.
   if (on_device) MPQC_T_CUDA(cudaDeviceSynchronize());
@@ -504,94 +536,258 @@ int upload_impl(mpqc_t_handle* h, const mpqc_t_problem* p, bool on_device, const
   return MPQC_T_OK;
 }
 
-#define MPQC_T_BLAS(expr)                                                                   \
-  do {                                                                                      \
-    cublasStatus_t _bs = (expr);                                                            \
-    if (_bs != CUBLAS_STATUS_SUCCESS) {                                                     \
-      char _buf[256];                                                                       \
-      snprintf(_buf, sizeof(_buf), "%s -> cuBLAS status %d", #expr, (int)_bs);              \
-      return fail(_bs == CUBLAS_STATUS_ALLOC_FAILED ? MPQC_T_ERR_OOM : MPQC_T_ERR_CUDA, _buf, __FILE__, __LINE__); \
-    }                                                                                       \
-  } while (0)
+// ---------------------------------------------------------------------------------------------------------------
+// Density-fitted inputs: the three integral classes are assembled on the device, straight into
+// the operand layouts, from the three-centre factors (what the reference's [df] formulas evaluate through TiledArray on
+// the host, ccsd_t.h:2210-2244 with is_df()) -- by the SAME TMA + DMMA pipeline as the W contraction, in its plain
+// batched NT-GEMM mode (w_contract.cuh, GemmParams::mode = 1).  No library GEMM is involved.
+//
+//   A[x][p][q][kap<v] = <x kap|p q> = sum_K Xai[K,p,x] Xab[K,kap,q]      C_(x,q)[p][kap],   L = XaiT[x], R = XabT[q]
+//   AT[x][p][q][kap]  = A[x][q][p][kap]                                  C_(x,p)[q][kap],   L = XaiT[x], R = XabT[p]
+//   GV[i][j][a][b]    = <ij|ab>     = sum_K Xai[K,a,i] Xai[K,b,j]        C_(i,j)[a][b],     L = XaiT[i], R = XaiT[j]
+//   B[y][z][r][v+l]   = <yz|lr>     = sum_K Xai[K,r,z] Xij[K,y,l]        C_(y,z)[r][l],     L = XaiT[z], R = XijT[y]
+// with the factor copies XaiT[x][a][K], XabT[q][kap][K] = Xab[K][kap][q], XijT[y][l][K] (K fastest, zero padded to Kx).
+// ---------------------------------------------------------------------------------------------------------------
+struct PlainGemm {
+  const double* L;   // [l_batches][M][Kx]
+  int64_t l_batches, M;
+  const double* R;   // [r_batches][N][Kx]
+  int64_t r_batches, N;
+  int64_t Kx;
+  int nbatch, l_div, l_mod, r_div, r_mod, o_div;
+  double* out;
+  int64_t out_s1, out_s2, ldw;
+};
 
-// Density-fitted upload: the three integral classes are assembled on the device, straight into the operand layouts,
-// from the three-centre factors (what the reference's [df] formulas evaluate through TiledArray on the host,
-// ccsd_t.h:2210-2244 with is_df()).  These are plain strided-batched library DGEMMs (cuBLAS), one-time, ~2 naux v^3 o
-// FLOPs for each of A and AT; the triples loop itself is unchanged.
+int launch_plain_gemm(mpqc_t_handle* h, const PlainGemm& g, int64_t* launches) {
+  if (g.nbatch <= 0 || g.M <= 0 || g.N <= 0) return MPQC_T_OK;
+  const int F = (int)((g.N + 7) / 8);
+  const int nnt = (F + kMaxNFrag - 1) / kMaxNFrag;
+  const int nfrag = (F + nnt - 1) / nnt;
+  const int tn = nfrag * 8;
+  const int skip_last = (nfrag >= 2 && nnt * nfrag - 1 >= F) ? 1 : 0;
+  const int nmt = (int)((g.M + kBM - 1) / kBM);
+  MPQC_T_CHECK((int64_t)g.nbatch * nmt * nnt < (1LL << 31), MPQC_T_ERR_INTERNAL, "too many tiles in one factor GEMM");
+  CUtensorMap tmL, tmR;
+  {
+    uint64_t dims[3] = {(uint64_t)g.Kx, (uint64_t)g.M, (uint64_t)g.l_batches};
+    uint64_t str[2] = {(uint64_t)g.Kx * 8, (uint64_t)g.M * g.Kx * 8};
+    uint32_t box[3] = {(uint32_t)kBK, (uint32_t)kBM, 1};
+    MPQC_T_TRY(encode_map(&tmL, const_cast<double*>(g.L), 3, dims, str, box));
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)g.Kx, (uint64_t)g.N, (uint64_t)g.r_batches};
+    uint64_t str[2] = {(uint64_t)g.Kx * 8, (uint64_t)g.N * g.Kx * 8};
+    uint32_t box[3] = {(uint32_t)kBK, (uint32_t)tn, 1};
+    MPQC_T_TRY(encode_map(&tmR, const_cast<double*>(g.R), 3, dims, str, box));
+  }
+  GemmParams P;
+  memset(&P, 0, sizeof(P));
+  P.v = (int)g.M;
+  P.o = 0;
+  P.Kp = (int)g.Kx;
+  P.kblocks = (int)((g.Kx + kBK - 1) / kBK);
+  P.tp = P.tq = 1;
+  P.npt = P.nqt = 1;
+  P.tn = tn;
+  P.nfrag = nfrag;
+  P.nnt = nnt;
+  P.skip_last = skip_last;
+  P.flat = 1;
+  P.nmt = nmt;
+  P.tiles_per_group = nmt * nnt;
+  P.total_tiles = g.nbatch * nmt * nnt;
+  P.main_tiles = g.nbatch * nmt * (nnt - skip_last);
+  P.rows_valid = kBM;
+  P.w = g.out;
+  P.mode = 1;
+  P.ncols = (int)g.N;
+  P.l_div = g.l_div;
+  P.l_mod = g.l_mod;
+  P.r_div = g.r_div;
+  P.r_mod = g.r_mod;
+  P.o_div = g.o_div;
+  P.out_s1 = g.out_s1;
+  P.out_s2 = g.out_s2;
+  P.ldw64 = g.ldw;
+  GemmKernelFn fn = gemm_kernel_for(nfrag);
+  MPQC_T_CHECK(fn != nullptr, MPQC_T_ERR_INTERNAL, "no GEMM kernel for this column-fragment count");
+  MPQC_T_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+  const int grid = std::min(h->num_sms, P.total_tiles);
+  fn<<<grid, kGemmThreads, kGemmSmemBytes, h->stream>>>(tmL, tmL, tmR, P);
+  MPQC_T_CUDA(cudaGetLastError());
+  if (launches) ++*launches;
+  return MPQC_T_OK;
+}
+
+// particle + hole part of the operand panels of occupied indices x0 .. x0+nx-1 into pool slots slot0 .. (consecutive)
+int build_panels(mpqc_t_handle* h, int x0, int nx, int slot0, int64_t* launches) {
+  const int64_t o = h->o, v = h->v, Kp = h->Kp;
+  const int64_t pstride = v * v * Kp;
+  PlainGemm g;
+  g.L = h->XaiT + (int64_t)x0 * v * h->Kx;   // batch entry b = (x - x0) * v + q
+  g.l_batches = nx;
+  g.M = v;
+  g.R = h->XabT;
+  g.r_batches = v;
+  g.N = v;
+  g.Kx = h->Kx;
+  g.nbatch = nx * (int)v;
+  g.l_div = (int)v;
+  g.l_mod = nx;
+  g.r_div = 1;
+  g.r_mod = (int)v;
+  g.o_div = (int)v;
+  // A[slot][p][q][kap]: row p has pitch v*Kp, batch entry (x, q) starts at slot*pstride + q*Kp
+  g.out = h->A + (int64_t)slot0 * pstride;
+  g.out_s1 = pstride;
+  g.out_s2 = Kp;
+  g.ldw = v * Kp;
+  MPQC_T_TRY(launch_plain_gemm(h, g, launches));
+  if (h->flat) {
+    // AT[slot][p][q][kap] = A[slot][q][p][kap]: batch entry (x, p), row q has pitch Kp
+    g.out = h->AT + (int64_t)slot0 * pstride;
+    g.out_s2 = v * Kp;
+    g.ldw = Kp;
+    MPQC_T_TRY(launch_plain_gemm(h, g, launches));
+  }
+  if (h->panel_mode) {
+    const int64_t total = v * v * o;
+    const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, 148 * 32);
+    for (int x = x0; x < x0 + nx; ++x) {
+      const int s = slot0 + (x - x0);
+      copy_hole_panel_kernel<<<blocks, 256, 0, h->stream>>>(h->T2raw, h->A + (int64_t)s * pstride, v, o, x, Kp, 0);
+      if (h->flat)
+        copy_hole_panel_kernel<<<blocks, 256, 0, h->stream>>>(h->T2raw, h->AT + (int64_t)s * pstride, v, o, x, Kp, 1);
+      MPQC_T_CUDA(cudaGetLastError());
+      if (launches) *launches += h->flat ? 2 : 1;
+    }
+  }
+  h->panels_built += nx;
+  return MPQC_T_OK;
+}
+
+// occupied block edge of the panel walk: the pool must hold the panels of three occupied blocks
+int panel_block_edge(const mpqc_t_handle* h) { return std::max(1, h->npanel / 3); }
+
 int upload_df_impl(mpqc_t_handle* h, const mpqc_t_df_problem* p, bool on_device, const CommView& cv, mpqc_t_stats* stats) {
   const int64_t o = h->o, v = h->v, Kp = h->Kp, naux = p->naux;
   cudaStream_t st = h->stream;
   int64_t launches = 0, h2d = 0;
   const double t0 = now_s();
   double t_copy = 0.0;
-  const BlasApi& bl = blas_api();
-  MPQC_T_CHECK(bl.ok, MPQC_T_ERR_CUDA, "density-fitted upload needs libcublas.so.12, which could not be loaded");
+  h->uploaded = false;
   if (on_device) MPQC_T_CUDA(cudaDeviceSynchronize());   // ordering contract for device-resident inputs (mpqc_t.h)
-  if (!h->blas) {
-    MPQC_T_BLAS(bl.Create(&h->blas));
-    MPQC_T_BLAS(bl.SetStream(h->blas, st));   // pointer mode defaults to host
+  const int64_t Kx = std::max<int64_t>(16, roundup(naux, 8));
+  h->Kx = Kx;
+  cudaFree(h->XaiT);
+  cudaFree(h->XabT);
+  cudaFree(h->T2raw);
+  h->XaiT = h->XabT = h->T2raw = nullptr;
+
+  // ---- resident or panel cache?  Resident when the whole operand fits beside everything else; otherwise the largest
+  //      occupied block edge (<= 8) whose 3 blocks of panels fit.  MPQC_T_DF_BLOCK / mpqc_t_set_df_block force it. ----
+  int block = h->df_block;
+  if (const char* env = getenv("MPQC_T_DF_BLOCK")) block = atoi(env);
+  const double panel_bytes = (double)v * v * Kp * 8.0;
+  const double factors = ((double)o * v + (double)v * v) * Kx * 8.0;
+  const double staging = on_device ? 0.0 : ((double)naux * v * v + (double)naux * v * o) * 8.0;   // raw factor copies
+  const double t2_bytes = (double)v * v * o * o * 8.0;
+  const double w_one = 3.0 * (double)v * v * (double)roundup(v, 16) * 8.0;
+  size_t free_b = 0, total_b = 0;
+  MPQC_T_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  int npanel = (int)o;
+  if (block > 0) {
+    npanel = (int)std::min<int64_t>(o, 3LL * block);
+  } else if (block == 0) {
+    const double resident = (double)o * panel_bytes + factors + staging + (on_device ? 0.0 : t2_bytes) + w_one;
+    if (resident > 0.80 * (double)free_b) {
+      const double room = 0.80 * (double)free_b - (factors + staging + t2_bytes + w_one);
+      const int fit = (int)std::floor(room / panel_bytes);
+      npanel = (int)std::min<int64_t>(o, std::max(3, std::min(24, fit / 3 * 3)));
+    }
   }
-  MPQC_T_CUDA(cudaMemsetAsync(h->A, 0, (size_t)o * v * v * Kp * sizeof(double), st));
+  const bool panel_mode = npanel < o;
+  MPQC_T_TRY(alloc_operands(h, npanel, factors + staging + (panel_mode || !on_device ? t2_bytes : 0.0)));
+  MPQC_T_CUDA(cudaMemsetAsync(h->A, 0, (size_t)npanel * v * v * Kp * sizeof(double), st));
+  if (h->flat) MPQC_T_CUDA(cudaMemsetAsync(h->AT, 0, (size_t)npanel * v * v * Kp * sizeof(double), st));
   MPQC_T_CUDA(cudaMemsetAsync(h->B, 0, (size_t)o * o * v * Kp * sizeof(double), st));
-  if (h->flat) MPQC_T_CUDA(cudaMemsetAsync(h->AT, 0, (size_t)o * v * v * Kp * sizeof(double), st));
 
   const double tc = now_s();
   const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   MPQC_T_CUDA(cudaMemcpyAsync(h->eps_occ, p->eps_occ, o * sizeof(double), kind, st));
   MPQC_T_CUDA(cudaMemcpyAsync(h->eps_vir, p->eps_vir, v * sizeof(double), kind, st));
   if (!on_device) h2d += (o + v) * 8;
-  Staged t1, t2, xab, xij, xai;
-  CommView solo;
-  MPQC_T_TRY(stage_in(t1, p->t1, (size_t)v * o, on_device, solo, st, &h2d));
-  MPQC_T_TRY(stage_in(t2, p->t2, (size_t)v * v * o * o, on_device, cv, st, &h2d));
-  MPQC_T_TRY(stage_in(xab, p->x_ab, (size_t)naux * v * v, on_device, cv, st, &h2d));
-  MPQC_T_TRY(stage_in(xij, p->x_ij, (size_t)naux * o * o, on_device, solo, st, &h2d));
-  MPQC_T_TRY(stage_in(xai, p->x_ai, (size_t)naux * v * o, on_device, cv, st, &h2d));
-  if (!on_device) {
-    MPQC_T_CUDA(cudaStreamSynchronize(st));
-    t_copy += now_s() - tc;
-  }
-  // XaiT[x][K][a] = Xai[K][a][x]  (unit stride on the virtual index for the GEMMs below)
-  DevBuf xait_owner;
-  MPQC_T_TRY(xait_owner.alloc((size_t)o * naux * v));
-  double* xait = xait_owner.p;
-  // in[kap = K][mid = a][j = x] -> out[x * naux*v + K * v + a]: generic transpose wants kap last, so treat
-  // (K,a) flattened as kap: in[(K a)][1][x] -> out[x][(K a)]
-  MPQC_T_TRY(launch_transpose(st, xai.ptr, xait, naux * v, 1, o, 1, naux * v, 0, 0, &launches));
-
-  // amplitude parts (same as the dense upload)
-  MPQC_T_TRY(launch_transpose(st, t1.ptr, h->T1T, v, 1, o, 1, v, 0, 0, &launches));
-  MPQC_T_TRY(launch_transpose(st, t2.ptr, h->B, v, v, o * o, 1, v * Kp, 0, Kp, &launches));
-  MPQC_T_TRY(launch_copy_hole(st, t2.ptr, h->A, v * v, o, o, v, v * Kp, Kp, v * v * Kp, v, -1.0, &launches));
-  if (h->flat)
-    MPQC_T_TRY(launch_copy_hole(st, t2.ptr, h->AT, v * v, o, o, v, Kp, v * Kp, v * v * Kp, v, -1.0, &launches));
-
-  const double one = 1.0, zero = 0.0;
-  const int iv = (int)v, io = (int)o, ik = (int)naux;
-  // All GEMMs below are column-major C_cm(m x n) = op(A_cm) op(B_cm); row-major targets are written as their transposes.
-  for (int64_t x = 0; x < o; ++x) {
-    const double* xt = xait + x * naux * v;                       // (a, K) column-major, ld = v
-    // A[x][p][q][kap] = sum_K Xai[K,p,x] Xab[K,q,kap]:  for each q: C_cm(kap, p), ldc = v*Kp
-    MPQC_T_BLAS(bl.DgemmStridedBatched(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, iv, iv, ik, &one, xab.ptr, iv * iv, v,
-                                          xt, iv, 0, &zero, h->A + x * v * v * Kp, (int)(v * Kp), Kp, iv));
-    ++launches;
-    if (h->flat) {
-      // AT[x][p][q][kap] = sum_K Xai[K,q,x] Xab[K,p,kap]:  for each p: C_cm(kap, q), ldc = Kp
-      MPQC_T_BLAS(bl.DgemmStridedBatched(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, iv, iv, ik, &one, xab.ptr, iv * iv, v,
-                                            xt, iv, 0, &zero, h->AT + x * v * v * Kp, (int)Kp, v * Kp, iv));
-      ++launches;
+  DevBuf xijt;
+  {
+    Staged t1, t2, xab, xij, xai;
+    CommView solo;
+    MPQC_T_TRY(stage_in(t1, p->t1, (size_t)v * o, on_device, solo, st, &h2d));
+    MPQC_T_TRY(stage_in(t2, p->t2, (size_t)v * v * o * o, on_device, cv, st, &h2d));
+    MPQC_T_TRY(stage_in(xab, p->x_ab, (size_t)naux * v * v, on_device, cv, st, &h2d));
+    MPQC_T_TRY(stage_in(xij, p->x_ij, (size_t)naux * o * o, on_device, solo, st, &h2d));
+    MPQC_T_TRY(stage_in(xai, p->x_ai, (size_t)naux * v * o, on_device, cv, st, &h2d));
+    if (!on_device) {
+      MPQC_T_CUDA(cudaStreamSynchronize(st));
+      t_copy += now_s() - tc;
     }
-    // GV[x][j][a][b] = sum_K Xai[K,a,x] Xai[K,b,j]:  for each j: C_cm(b, a) = XaiT[j](b,K) XaiT[x](a,K)^T
-    MPQC_T_BLAS(bl.DgemmStridedBatched(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, iv, iv, ik, &one, xait, iv, naux * v, xt,
-                                          iv, 0, &zero, h->GV + x * o * v * v, iv, v * v, io));
-    ++launches;
-    // B[y][x][r][v + l] = g_aijk[r,y,x,l] = sum_K Xij[K,y,l] Xai[K,r,x]:  for each y: C_cm(l, r), ldc = Kp
-    MPQC_T_BLAS(bl.DgemmStridedBatched(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, io, iv, ik, &one, xij.ptr, io * io, o, xt,
-                                          iv, 0, &zero, h->B + x * v * Kp + v, (int)Kp, o * v * Kp, io));
-    ++launches;
+    // factor copies with the auxiliary index fastest (one 128-byte TMA box row per 16 K), zero padded to Kx
+    MPQC_T_CUDA(cudaMalloc(&h->XaiT, (size_t)o * v * Kx * sizeof(double)));
+    MPQC_T_CUDA(cudaMalloc(&h->XabT, (size_t)v * v * Kx * sizeof(double)));
+    MPQC_T_TRY(xijt.alloc((size_t)o * o * Kx));
+    MPQC_T_CUDA(cudaMemsetAsync(h->XaiT, 0, (size_t)o * v * Kx * sizeof(double), st));
+    MPQC_T_CUDA(cudaMemsetAsync(h->XabT, 0, (size_t)v * v * Kx * sizeof(double), st));
+    MPQC_T_CUDA(cudaMemsetAsync(xijt.p, 0, (size_t)o * o * Kx * sizeof(double), st));
+    // XaiT[x][a][K] = Xai[K][a][x]:      in[kap=K][mid=a][j=x]    -> out[x * v*Kx + a * Kx + K]
+    MPQC_T_TRY(launch_transpose(st, xai.ptr, h->XaiT, naux, v, o, 1, v * Kx, 0, Kx, &launches));
+    // XabT[q][kap][K] = Xab[K][kap][q]:  in[kap=K][mid=kap][j=q]  -> out[q * v*Kx + kap * Kx + K]
+    MPQC_T_TRY(launch_transpose(st, xab.ptr, h->XabT, naux, v, v, 1, v * Kx, 0, Kx, &launches));
+    // XijT[y][l][K] = Xij[K][y][l]:      in[kap=K][mid=y][j=l]    -> out[y * o*Kx + l * Kx + K]
+    MPQC_T_TRY(launch_transpose(st, xij.ptr, xijt.p, naux, o, o, 1, Kx, 0, o * Kx, &launches));
+
+    // amplitude parts (same as the dense upload)
+    MPQC_T_TRY(launch_transpose(st, t1.ptr, h->T1T, v, 1, o, 1, v, 0, 0, &launches));
+    MPQC_T_TRY(launch_transpose(st, t2.ptr, h->B, v, v, o * o, 1, v * Kp, 0, Kp, &launches));
+    if (panel_mode) {
+      // the hole part of a panel is written when the panel is built: keep t2 on the device
+      MPQC_T_CUDA(cudaMalloc(&h->T2raw, (size_t)v * v * o * o * sizeof(double)));
+      MPQC_T_CUDA(cudaMemcpyAsync(h->T2raw, t2.ptr, (size_t)v * v * o * o * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      MPQC_T_CUDA(cudaMalloc(&h->slot_map_dev, (size_t)o * sizeof(int)));
+    } else {
+      MPQC_T_TRY(launch_copy_hole(st, t2.ptr, h->A, v * v, o, o, v, v * Kp, Kp, v * v * Kp, v, -1.0, &launches));
+      if (h->flat)
+        MPQC_T_TRY(launch_copy_hole(st, t2.ptr, h->AT, v * v, o, o, v, Kp, v * Kp, v * v * Kp, v, -1.0, &launches));
+    }
+    MPQC_T_CUDA(cudaStreamSynchronize(st));   // staged raw inputs are released here
+  }
+
+  PlainGemm g;
+  // GV[i][j][a][b]
+  g.L = h->XaiT; g.l_batches = o; g.M = v;
+  g.R = h->XaiT; g.r_batches = o; g.N = v;
+  g.Kx = Kx;
+  g.nbatch = (int)(o * o);
+  g.l_div = (int)o; g.l_mod = (int)o; g.r_div = 1; g.r_mod = (int)o; g.o_div = 1;
+  g.out = h->GV; g.out_s1 = v * v; g.out_s2 = 0; g.ldw = v;
+  MPQC_T_TRY(launch_plain_gemm(h, g, &launches));
+  // B[y][z][r][v + l]
+  g.L = h->XaiT; g.l_batches = o; g.M = v;
+  g.R = xijt.p; g.r_batches = o; g.N = o;
+  g.nbatch = (int)(o * o);
+  g.l_div = 1; g.l_mod = (int)o; g.r_div = (int)o; g.r_mod = (int)o; g.o_div = 1;
+  g.out = h->B + v; g.out_s1 = v * Kp; g.out_s2 = 0; g.ldw = Kp;
+  MPQC_T_TRY(launch_plain_gemm(h, g, &launches));
+  // operand panels: all of them now (resident), or on demand while the units are walked (panel cache)
+  if (!panel_mode) {
+    for (int x0 = 0; x0 < (int)o; x0 += 16) MPQC_T_TRY(build_panels(h, x0, std::min(16, (int)o - x0), x0, &launches));
   }
   MPQC_T_CUDA(cudaStreamSynchronize(st));
   MPQC_T_CUDA(cudaGetLastError());
+  if (!panel_mode) {   // the factor copies are only needed again in panel mode
+    cudaFree(h->XaiT);
+    cudaFree(h->XabT);
+    h->XaiT = h->XabT = nullptr;
+  }
   h->uploaded = true;
   if (stats) {
     double tot = now_s() - t0;
@@ -599,6 +795,119 @@ int upload_df_impl(mpqc_t_handle* h, const mpqc_t_df_problem* p, bool on_device,
     stats->seconds_relayout += tot - t_copy;
     stats->kernel_launches += launches;
     stats->bytes_h2d += h2d;
+  }
+  return MPQC_T_OK;
+}
+
+// Panel-cache mode: make the panels of the occupied indices in `need` (sorted, unique) resident, evicting the least
+// recently used panels that are not needed now, and refresh the device slot map.  All on the handle's stream, so the
+// kernels that still read an evicted slot have finished before it is overwritten.
+int ensure_panels(mpqc_t_handle* h, const std::vector<int>& need, int64_t* launches) {
+  MPQC_T_CHECK((int)need.size() <= h->npanel, MPQC_T_ERR_INTERNAL, "panel pool smaller than one unit group");
+  std::vector<char> wanted((size_t)h->o, 0);
+  for (int x : need) wanted[(size_t)x] = 1;
+  ++h->stamp;
+  bool changed = false;
+  for (int x : need) {
+    int s = h->slot_of[(size_t)x];
+    if (s < 0) {
+      // victim: a free slot, else the least recently used slot whose panel is not needed by this group
+      int victim = -1;
+      for (int q = 0; q < h->npanel; ++q) {
+        const int xq = h->x_of_slot[(size_t)q];
+        if (xq < 0) { victim = q; break; }
+        if (wanted[(size_t)xq]) continue;
+        if (victim < 0 || h->slot_stamp[(size_t)q] < h->slot_stamp[(size_t)victim]) victim = q;
+      }
+      MPQC_T_CHECK(victim >= 0, MPQC_T_ERR_INTERNAL, "no evictable panel slot");
+      if (h->x_of_slot[(size_t)victim] >= 0) h->slot_of[(size_t)h->x_of_slot[(size_t)victim]] = -1;
+      h->x_of_slot[(size_t)victim] = x;
+      h->slot_of[(size_t)x] = victim;
+      MPQC_T_TRY(build_panels(h, x, 1, victim, launches));
+      s = victim;
+      changed = true;
+    }
+    h->slot_stamp[(size_t)s] = h->stamp;
+  }
+  if (changed)   // pageable source: the runtime stages it before returning, so slot_of may change again right away
+    MPQC_T_CUDA(cudaMemcpyAsync(h->slot_map_dev, h->slot_of.data(), (size_t)h->o * sizeof(int), cudaMemcpyHostToDevice,
+                                h->stream));
+  return MPQC_T_OK;
+}
+
+// key of the occupied-block triple a unit belongs to (block edge bo): units with equal keys need at most 3 bo panels
+inline int64_t block_key(int i, int j, int k, int bo) {
+  const int64_t nb = 4096 / bo + 2;
+  return ((int64_t)(i / bo) * nb + (j / bo)) * nb + (k / bo);
+}
+
+// Panel-cache mode of run_units: the units are processed grouped by occupied-block triple (sorted by key, so
+// consecutive groups share their leading blocks and the LRU pool keeps those panels); before a group runs, the
+// panels it needs are built on the stream.  Results return in the caller's unit order.
+int run_units_panels(mpqc_t_handle* h, const std::vector<int>& tri, int64_t n, int batch, double* unit_e_host,
+                     mpqc_t_stats* stats, double* vblock_dev) {
+  const int bo = panel_block_edge(h);
+  std::vector<int64_t> order((size_t)n);
+  for (int64_t u = 0; u < n; ++u) order[(size_t)u] = u;
+  std::vector<int64_t> key((size_t)n);
+  for (int64_t u = 0; u < n; ++u) key[(size_t)u] = block_key(tri[3 * u], tri[3 * u + 1], tri[3 * u + 2], bo);
+  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return key[(size_t)a] < key[(size_t)b]; });
+  std::vector<int> tri_sorted((size_t)n * 3);
+  for (int64_t q = 0; q < n; ++q)
+    for (int c = 0; c < 3; ++c) tri_sorted[3 * q + c] = tri[3 * order[(size_t)q] + c];
+  MPQC_T_CUDA(cudaMemcpyAsync(h->triples_dev, tri_sorted.data(), tri_sorted.size() * sizeof(int), cudaMemcpyHostToDevice,
+                              h->stream));
+  EventList events;
+  cudaEvent_t e_begin, e_end;
+  MPQC_T_TRY(events.add(&e_begin));
+  MPQC_T_TRY(events.add(&e_end));
+  MPQC_T_CUDA(cudaEventRecord(e_begin, h->stream));
+  int64_t launches = 0;
+  const int64_t built0 = h->panels_built;
+  for (int64_t g0 = 0; g0 < n;) {
+    int64_t g1 = g0;
+    std::vector<int> need;
+    while (g1 < n && key[(size_t)order[(size_t)g1]] == key[(size_t)order[(size_t)g0]]) {
+      for (int c = 0; c < 3; ++c) need.push_back(tri_sorted[3 * g1 + c]);
+      ++g1;
+    }
+    std::sort(need.begin(), need.end());
+    need.erase(std::unique(need.begin(), need.end()), need.end());
+    MPQC_T_TRY(ensure_panels(h, need, &launches));
+    for (int64_t off = g0; off < g1; off += batch) {
+      const int nb = (int)std::min<int64_t>(batch, g1 - off);
+      MPQC_T_TRY(launch_gemm(h, nb, h->triples_dev + 3 * off));
+      MPQC_T_TRY(launch_energy(h, nb, h->triples_dev + 3 * off, h->unit_e_dev + off));
+      launches += 3;
+      if (vblock_dev) {
+        t_energy_vblock_kernel<<<(h->ntt + 255) / 256, 256, 0, h->stream>>>(h->partial, h->ntt, nb,
+                                                                          h->triples_dev + 3 * off, vblock_dev);
+        MPQC_T_CUDA(cudaGetLastError());
+        ++launches;
+      }
+    }
+    g0 = g1;
+  }
+  MPQC_T_CUDA(cudaEventRecord(e_end, h->stream));
+  std::vector<double> ue((size_t)n);
+  MPQC_T_CUDA(cudaMemcpyAsync(ue.data(), h->unit_e_dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  MPQC_T_CUDA(cudaStreamSynchronize(h->stream));
+  MPQC_T_CUDA(cudaGetLastError());
+  for (int64_t q = 0; q < n; ++q) unit_e_host[order[(size_t)q]] = ue[(size_t)q];
+  if (stats) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e_begin, e_end);
+    stats->seconds_compute += ms * 1e-3;
+    stats->units += n;
+    stats->kernel_launches += launches;
+    stats->flops += (double)n * mpqc_t_unit_flops(h->o, h->v);
+    const double mpad = (double)h->nmt * kBM, npad = (double)h->nnt * h->tn - 8.0 * h->skip_last;
+    // executed: the triples themselves + the panels built for them (2 naux v^3 each, twice in flat mode)
+    stats->flops_executed += (double)n * 3.0 * 2.0 * 2.0 * mpad * npad * (double)h->Kp +
+                             (double)(h->panels_built - built0) * 2.0 * (double)h->Kx * (double)h->v * h->v * h->v *
+                                 (h->flat ? 2.0 : 1.0);
+    stats->bytes_d2h += n * 8;
+    stats->bytes_h2d += n * 12;
   }
   return MPQC_T_OK;
 }
@@ -621,6 +930,7 @@ int run_units(mpqc_t_handle* h, const UnitIndex& ux, const int64_t* units, int64
   MPQC_T_TRY(ensure_units(h, n));
   std::vector<int> tri((size_t)n * 3);
   for (int64_t u = 0; u < n; ++u) ux.triple(units[u], tri[3 * u], tri[3 * u + 1], tri[3 * u + 2]);
+  if (h->panel_mode) return run_units_panels(h, tri, n, batch, unit_e_host, stats, vblock_dev);
   MPQC_T_CUDA(cudaMemcpyAsync(h->triples_dev, tri.data(), tri.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
 
   const int64_t nbatches = (n + batch - 1) / batch;
@@ -819,38 +1129,14 @@ int mpqc_t_create(mpqc_t_handle** out, int64_t o, int64_t v, int32_t device) {
   h->num_sms = prop.multiProcessorCount;
   int rc = [&]() -> int {
     MPQC_T_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    {
-      // "flat" mode keeps a transposed copy AT of the big operand so both GEMM terms read 128 consecutive
-      // flattened (p,q) rows (no row-patch padding).  Use it when 2|A| + the rest leaves >= 25% of free HBM.
-      size_t free_b = 0, total_b = 0;
-      MPQC_T_CUDA(cudaMemGetInfo(&free_b, &total_b));
-      const double a_bytes = (double)o * v * v * h->Kp * 8.0;
-      const double rest = (double)o * o * v * h->Kp * 8.0 + (double)o * o * v * v * 8.0 + 8e9;
-      const char* env = getenv("MPQC_T_FLAT");
-      h->flat = (2.0 * a_bytes + rest) < 0.75 * (double)free_b ? 1 : 0;
-      if (env) h->flat = atoi(env) != 0;
-      // feasibility: the accepted (o, v) range is far wider than what one device can hold.  Refuse here, with the
-      // numbers, instead of failing inside some later cudaMalloc: resident operands + the W workspace of ONE triple.
-      const double w_one = 3.0 * (double)v * v * (double)roundup(v, 16) * 8.0;
-      const double need = a_bytes * (h->flat ? 2.0 : 1.0) + (rest - 8e9) + w_one;
-      if (need > 0.98 * (double)free_b) {
-        char buf[320];
-        snprintf(buf, sizeof(buf),
-                 "problem o=%lld v=%lld needs %.1f GB of device memory (operands %.1f GB + W workspace %.1f GB per triple) "
-                 "but only %.1f GB are free on device %d",
-                 (long long)o, (long long)v, need * 1e-9, (need - w_one) * 1e-9, w_one * 1e-9, (double)free_b * 1e-9, device);
-        return fail(MPQC_T_ERR_OOM, buf, __FILE__, __LINE__);
-      }
-    }
-    MPQC_T_CUDA(cudaMalloc(&h->A, (size_t)o * v * v * h->Kp * sizeof(double)));
-    if (h->flat) MPQC_T_CUDA(cudaMalloc(&h->AT, (size_t)o * v * v * h->Kp * sizeof(double)));
+    // the big operand A (and its transposed copy) is allocated by the first upload: only then is it known whether
+    // all o panels are resident (dense inputs; density-fitted inputs that fit) or a panel cache is used
     MPQC_T_CUDA(cudaMalloc(&h->B, (size_t)o * o * v * h->Kp * sizeof(double)));
     MPQC_T_CUDA(cudaMalloc(&h->GV, (size_t)o * o * v * v * sizeof(double)));
     MPQC_T_CUDA(cudaMalloc(&h->T1T, (size_t)o * v * sizeof(double)));
     MPQC_T_CUDA(cudaMalloc(&h->eps_occ, (size_t)o * sizeof(double)));
     MPQC_T_CUDA(cudaMalloc(&h->eps_vir, (size_t)v * sizeof(double)));
     MPQC_T_TRY(plan(h));
-    MPQC_T_TRY(make_maps(h));
     std::vector<uint8_t> sets((size_t)h->ntt * 4);
     size_t n = 0;
     for (int a = 0; a < h->ntile; ++a)
@@ -895,7 +1181,10 @@ int mpqc_t_destroy(mpqc_t_handle* h) {
   cudaFree(h->tile_sets);
   cudaFree(h->triples_dev);
   cudaFree(h->unit_e_dev);
-  if (h->blas && blas_api().ok) blas_api().Destroy(h->blas);
+  cudaFree(h->slot_map_dev);
+  cudaFree(h->XaiT);
+  cudaFree(h->XabT);
+  cudaFree(h->T2raw);
   if (h->stream) cudaStreamDestroy(h->stream);
   cudaGetLastError();
   delete h;
@@ -903,6 +1192,52 @@ int mpqc_t_destroy(mpqc_t_handle* h) {
 }
 
 void* mpqc_t_stream(mpqc_t_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int mpqc_t_query(mpqc_t_handle* h, int32_t what, int64_t* value) {
+  MPQC_T_CHECK(h != nullptr && value != nullptr, MPQC_T_ERR_BAD_ARG, "handle or output is NULL");
+  switch (what) {
+    case MPQC_T_QUERY_PANEL_SLOTS: *value = h->npanel; break;
+    case MPQC_T_QUERY_PANEL_MODE: *value = h->panel_mode ? 1 : 0; break;
+    case MPQC_T_QUERY_FLAT: *value = h->flat; break;
+    case MPQC_T_QUERY_PANELS_BUILT: *value = h->panels_built; break;
+    case MPQC_T_QUERY_PANEL_BLOCK: *value = h->panel_mode ? panel_block_edge(h) : h->o; break;
+    default: return fail(MPQC_T_ERR_BAD_ARG, "unknown query", __FILE__, __LINE__);
+  }
+  return MPQC_T_OK;
+}
+
+int mpqc_t_set_df_block(mpqc_t_handle* h, int32_t block) {
+  MPQC_T_CHECK(h != nullptr, MPQC_T_ERR_BAD_ARG, "handle is NULL");
+  MPQC_T_CHECK(block >= -1 && block <= 4096, MPQC_T_ERR_BAD_ARG, "df block must be -1 (resident), 0 (automatic) or a block edge");
+  h->df_block = block;
+  return MPQC_T_OK;
+}
+
+int mpqc_t_plan_df(int64_t o, int64_t v, int64_t naux, int32_t block, int32_t flat, mpqc_t_df_plan_info* out) {
+  MPQC_T_CHECK(out != nullptr, MPQC_T_ERR_BAD_ARG, "plan output is NULL");
+  MPQC_T_CHECK(o >= 1 && v >= 1 && naux >= 1 && o <= 4096 && v <= 2040 && block >= 0, MPQC_T_ERR_BAD_ARG,
+               "need 1 <= o <= 4096, 1 <= v <= 2040, naux >= 1, block >= 0");
+  memset(out, 0, sizeof(*out));
+  const double Kp = (double)std::max<int64_t>(16, roundup(v + o, 8)), Kx = (double)std::max<int64_t>(16, roundup(naux, 8));
+  const int npanel = block > 0 ? (int)std::min<int64_t>(o, 3LL * block) : (int)o;
+  out->npanel = npanel;
+  out->panel_mode = npanel < o;
+  out->block = out->panel_mode ? std::max(1, npanel / 3) : (int32_t)o;
+  out->flat = flat != 0;
+  out->bytes_panels = (double)npanel * v * v * Kp * 8.0 * (flat ? 2.0 : 1.0);
+  out->bytes_b = (double)o * o * v * Kp * 8.0;
+  out->bytes_gv = (double)o * o * v * v * 8.0;
+  out->bytes_t2 = out->panel_mode ? (double)v * v * o * o * 8.0 : 0.0;
+  out->bytes_factors = out->panel_mode ? ((double)o * v + (double)v * v) * Kx * 8.0 : 0.0;
+  out->bytes_w_workspace = 3.0 * (double)v * v * (double)roundup(v, 16) * 8.0;
+  out->bytes_total = out->bytes_panels + out->bytes_b + out->bytes_gv + out->bytes_t2 + out->bytes_factors + out->bytes_w_workspace;
+  // panels built over the whole job ~ o^3 / (6 block^2) (one block of panels per occupied-block triple), 2 Kx v^3 FLOPs
+  // each, against 2 o^3 v^3 (v+o) for the triples
+  const double bo = (double)out->block;
+  out->build_flop_fraction = out->panel_mode ? (Kx / (6.0 * bo * bo * (double)(v + o))) * (flat ? 2.0 : 1.0)
+                                             : (double)o * 2.0 * Kx * v * v * v * (flat ? 2.0 : 1.0) / mpqc_t_flops(o, v);
+  return MPQC_T_OK;
+}
 
 int mpqc_t_upload(mpqc_t_handle* h, const mpqc_t_problem* p, int32_t on_device, mpqc_t_stats* stats) {
   MPQC_T_CHECK(h != nullptr, MPQC_T_ERR_BAD_ARG, "handle is NULL");
@@ -1055,6 +1390,12 @@ int mpqc_t_debug_w(mpqc_t_handle* h, int32_t i, int32_t j, int32_t k, double* w_
   MPQC_T_TRY(ensure_units(h, 1));
   int tri[3] = {i, j, k};
   MPQC_T_CUDA(cudaMemcpyAsync(h->triples_dev, tri, sizeof(tri), cudaMemcpyHostToDevice, h->stream));
+  if (h->panel_mode) {
+    std::vector<int> need = {i, j, k};
+    std::sort(need.begin(), need.end());
+    need.erase(std::unique(need.begin(), need.end()), need.end());
+    MPQC_T_TRY(ensure_panels(h, need, nullptr));
+  }
   MPQC_T_TRY(launch_gemm(h, 1, h->triples_dev));
   const int64_t v = h->v, ldw = h->ldw;
   std::vector<double> n((size_t)3 * v * v * ldw);
@@ -1160,6 +1501,7 @@ int energy_impl(const int64_t prob_o, const int64_t prob_v, const UploadFn& uplo
     mpqc_t_handle* h = nullptr;
     const double tw0 = now_s();
     int rc = mpqc_t_create(&h, prob_o, prob_v, devs[g]);
+    if (rc == MPQC_T_OK) h->df_block = opt.df_block;
     cudaStream_t cst = nullptr;                       // stream of this worker's collectives
     if (exchange) {
       cudaSetDevice(devs[g]);
@@ -1175,7 +1517,43 @@ int energy_impl(const int64_t prob_o, const int64_t prob_v, const UploadFn& uplo
     if (rc == MPQC_T_OK) rc = upload(h, cv, &gs);
     const double tw2 = now_s();
     std::vector<int64_t> done_idx;     // job positions this worker produced
-    if (rc == MPQC_T_OK) {
+    if (rc == MPQC_T_OK && h->panel_mode) {
+      // Panel-cache mode: shard by occupied-block triple, not by unit -- a worker that holds a group's panels runs
+      // the whole group.  Groups are dealt largest-first to the least loaded worker (same answer on every rank).
+      const int bo = panel_block_edge(h);
+      std::vector<std::pair<int64_t, int64_t>> keyed((size_t)count);   // (group key, job position)
+      for (int64_t q = 0; q < count; ++q) {
+        int i, j, k;
+        ux.triple(opt.unit_first + q * stride, i, j, k);
+        keyed[(size_t)q] = std::make_pair(block_key(i, j, k, bo), q);
+      }
+      std::sort(keyed.begin(), keyed.end());
+      std::vector<std::pair<int64_t, int64_t>> groups;                  // (size, first index into keyed)
+      for (int64_t a = 0; a < count;) {
+        int64_t b = a;
+        while (b < count && keyed[(size_t)b].first == keyed[(size_t)a].first) ++b;
+        groups.push_back(std::make_pair(b - a, a));
+        a = b;
+      }
+      std::stable_sort(groups.begin(), groups.end(),
+                       [](const std::pair<int64_t, int64_t>& x, const std::pair<int64_t, int64_t>& y) { return x.first > y.first; });
+      std::vector<int64_t> load((size_t)W, 0), mine, idx;
+      for (const auto& gsz : groups) {
+        const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        load[(size_t)w] += gsz.first;
+        if (w == wrank)
+          for (int64_t a = gsz.second; a < gsz.second + gsz.first; ++a) mine.push_back(keyed[(size_t)a].second);
+      }
+      idx.resize(mine.size());
+      std::vector<double> e(mine.size());
+      for (size_t q = 0; q < mine.size(); ++q) idx[q] = opt.unit_first + mine[q] * stride;
+      rc = run_units(h, ux, idx.data(), (int64_t)idx.size(), opt.batch, e.data(), &gs, profile);
+      if (rc == MPQC_T_OK)
+        for (size_t q = 0; q < mine.size(); ++q) {
+          unit_e[(size_t)mine[q]] = e[q];
+          done_idx.push_back(mine[q]);
+        }
+    } else if (rc == MPQC_T_OK) {
       // static share
       std::vector<int64_t> mine, idx;
       for (int64_t q = wrank; q < static_n; q += W) mine.push_back(q);

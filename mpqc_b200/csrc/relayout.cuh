@@ -58,6 +58,21 @@ copy_hole_kernel(const double* __restrict__ in, double* __restrict__ out, int64_
   }
 }
 
+// hole part of ONE operand panel (panel-cache mode): out[row(p,q)][v + l] = -t2[p][q][x][l], with row(p,q) = p*v + q
+// (panel A_x) or q*v + p (transposed copy AT_x)
+__global__ void __launch_bounds__(256)
+copy_hole_panel_kernel(const double* __restrict__ t2, double* __restrict__ panel, int64_t v, int64_t o, int64_t x,
+                       int64_t Kp, int transposed) {
+  const int64_t total = v * v * o;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t l = idx % o, pq = idx / o;
+    const int64_t pp = pq / v, qq = pq % v;
+    const int64_t row = transposed ? qq * v + pp : pq;
+    panel[row * Kp + v + l] = -__ldg(t2 + (pq * o + x) * o + l);
+  }
+}
+
 inline int launch_transpose(cudaStream_t st, const double* in, double* out, int64_t nk, int64_t nmid,
                             int64_t nj, int64_t jdiv, int64_t s1, int64_t s2, int64_t s3,
                             int64_t* launches) {

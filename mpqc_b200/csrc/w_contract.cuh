@@ -65,6 +65,16 @@ struct GemmParams {
   int rows_valid;             // tp * tq
   const int* triples;         // [nbatch][3] (i,j,k) of this launch
   double* w;                  // [nbatch][3][v*v*ldw]
+  const int* a_slot;          // panel-cache mode: occupied index x -> slot of A_x / AT_x in the panel pool (NULL: slot = x)
+  // ---- mode 1: plain batched NT GEMM on the same pipeline,  C_b[m][n] = sum_kap L_lb[m][kap] * R_rb[n][kap]
+  //      (used to assemble the integral classes from the three-centre factors, df_build.cuh).  tmA_n maps L as
+  //      (kap, m, batch) with a (16, 128, 1) box, tmB maps R as (kap, n, batch) with a (16, tn, 1) box;
+  //      lb = (b / l_div) % l_mod, rb = (b / r_div) % r_mod; C_b = w + (b / o_div) * out_s1 + (b % o_div) * out_s2,
+  //      row pitch ldw64, valid rows m < v, valid columns n < ncols.
+  int mode;                   // 0: W contraction (two terms, three groups), 1: plain NT GEMM (one term)
+  int ncols;                  // valid output columns (mode 0: v)
+  int l_div, l_mod, r_div, r_mod, o_div;
+  long long out_s1, out_s2, ldw64;
 };
 
 // sigma: MMA row/col index g (0..7) -> row inside the 8-row group.  Pairs (2h, 2h+1) map to rows
@@ -89,6 +99,21 @@ __device__ __forceinline__ void decode_tile(const GemmParams& P, int tile, int& 
   // (A_i: g = 0,1 term 0;  AT_j: g = 0,2 term 1;  A_k / AT_k: g = 2 / g = 1) while they are still in L2
   g = t % 3;
   t /= 3;
+  mt = t % P.nmt;
+  b = t / P.nmt;
+}
+
+// mode 1: column tile fastest (main tiles first, like above), then row tile, then batch entry
+__device__ __forceinline__ void decode_tile_plain(const GemmParams& P, int tile, int& b, int& mt, int& nt) {
+  int t;
+  if (tile < P.main_tiles) {
+    const int nn = P.nnt - P.skip_last;
+    nt = tile % nn;
+    t = tile / nn;
+  } else {
+    nt = P.nnt - 1;
+    t = tile - P.main_tiles;
+  }
   mt = t % P.nmt;
   b = t / P.nmt;
 }
@@ -210,16 +235,24 @@ __device__ __forceinline__ void producer_loop(const GemmParams& P, const CUtenso
       tma_prefetch_desc(tmB);
       int stage = 0;
       uint32_t phase = 0;
+      const int nterms = P.mode == 0 ? 2 : 1;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         int b, g, mt, nt;
-        decode_tile(P, tile, b, g, mt, nt);
-        const int i = P.triples[3 * b + 0], j = P.triples[3 * b + 1], k = P.triples[3 * b + 2];
-        int x1, yz1, x2, yz2;
-        if (g == 0)      { x1 = i; yz1 = j * P.o + k; x2 = j; yz2 = i * P.o + k; }
-        else if (g == 1) { x1 = i; yz1 = k * P.o + j; x2 = k; yz2 = i * P.o + j; }
-        else             { x1 = k; yz1 = j * P.o + i; x2 = j; yz2 = k * P.o + i; }
+        int x1, yz1, x2 = 0, yz2 = 0;
+        if (P.mode == 0) {
+          decode_tile(P, tile, b, g, mt, nt);
+          const int i = P.triples[3 * b + 0], j = P.triples[3 * b + 1], k = P.triples[3 * b + 2];
+          if (g == 0)      { x1 = i; yz1 = j * P.o + k; x2 = j; yz2 = i * P.o + k; }
+          else if (g == 1) { x1 = i; yz1 = k * P.o + j; x2 = k; yz2 = i * P.o + j; }
+          else             { x1 = k; yz1 = j * P.o + i; x2 = j; yz2 = k * P.o + i; }
+          if (P.a_slot) { x1 = P.a_slot[x1]; x2 = P.a_slot[x2]; }
+        } else {
+          decode_tile_plain(P, tile, b, mt, nt);
+          x1 = (b / P.l_div) % P.l_mod;
+          yz1 = (b / P.r_div) % P.r_mod;
+        }
         const int p0 = (mt / P.nqt) * P.tp, q0 = (mt % P.nqt) * P.tq, r0 = nt * P.tn, m0 = mt * kBM;
-        for (int term = 0; term < 2; ++term) {
+        for (int term = 0; term < nterms; ++term) {
           for (int kb = 0; kb < P.kblocks; kb += kSub) {
             const int nsub = (P.kblocks - kb) < kSub ? (P.kblocks - kb) : kSub;
             mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
@@ -258,7 +291,7 @@ __device__ __forceinline__ void consume_tiles(const GemmParams& P, int& tile, co
                                               const uint32_t (&a_off_n)[2], const uint32_t (&a_off_t)[2], const int warp,
                                               const int lane, const int sg, const int kq) {
   const int kblocks = P.kblocks;
-  const int nblk = 2 * kblocks;                       // k-blocks per tile (two terms)
+  const int nblk = (P.mode == 0 ? 2 : 1) * kblocks;   // k-blocks per tile (two terms in the W contraction)
   const bool half_last = (P.Kp % kBK) != 0;            // Kp % 16 == 8: last block of a term is half filled
   for (; tile < tile_end; tile += gridDim.x) {
     double acc[2][NFRAG][2];
@@ -299,16 +332,22 @@ __device__ __forceinline__ void consume_tiles(const GemmParams& P, int& tile, co
     }
 
     // ---- epilogue: registers -> N_g[p][q][r0 + col] (32-byte sector-aligned runs) ----
-    int b, g, mt, nt;
-    decode_tile(P, tile, b, g, mt, nt);
+    int b, g = 0, mt, nt;
+    if (P.mode == 0) decode_tile(P, tile, b, g, mt, nt);
+    else decode_tile_plain(P, tile, b, mt, nt);
     const int p0 = (mt / P.nqt) * P.tp, q0 = (mt % P.nqt) * P.tq, r0 = nt * P.tn;
-    double* wg = P.w + ((int64_t)(b * 3 + g)) * P.v * P.v * P.ldw;
+    double* wg = P.mode == 0 ? P.w + ((int64_t)(b * 3 + g)) * P.v * P.v * P.ldw
+                             : P.w + (int64_t)(b / P.o_div) * P.out_s1 + (int64_t)(b % P.o_div) * P.out_s2;
+    const int64_t pitch = P.mode == 0 ? (int64_t)P.ldw : (int64_t)P.ldw64;
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi) {
       const int m = 16 * warp + 8 * mi + sg;
-      int64_t pq;          // flattened p*v + q of this row
+      int64_t pq;          // flattened p*v + q of this row (mode 1: the row index)
       bool row_ok;
-      if (P.flat) {
+      if (P.mode != 0) {
+        pq = (int64_t)mt * kBM + m;
+        row_ok = pq < (int64_t)P.v;
+      } else if (P.flat) {
         pq = (int64_t)mt * kBM + m;
         row_ok = pq < (int64_t)P.v * P.v;
       } else {
@@ -316,14 +355,14 @@ __device__ __forceinline__ void consume_tiles(const GemmParams& P, int& tile, co
         pq = (int64_t)p * P.v + qq;
         row_ok = (m < P.rows_valid) && (p < P.v) && (qq < P.v);
       }
-      double* row = wg + pq * P.ldw + r0;
+      double* row = wg + pq * pitch + r0;
       if (row_ok) {
 #pragma unroll
         for (int ni = 0; ni < NFRAG - SKIP; ++ni) {
           // C fragment columns 2*kq, 2*kq+1 of the MMA -> tile columns 8*ni + sigma(2kq), sigma(2kq+1)
           const int c0 = 8 * ni + kq, c1 = 8 * ni + kq + 4;
-          if (r0 + c0 < P.v) row[c0] = acc[mi][ni][0];
-          if (r0 + c1 < P.v) row[c1] = acc[mi][ni][1];
+          if (r0 + c0 < P.ncols) row[c0] = acc[mi][ni][0];
+          if (r0 + c1 < P.ncols) row[c1] = acc[mi][ni][1];
         }
       }
     }

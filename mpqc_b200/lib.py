@@ -41,7 +41,7 @@ class Options(C.Structure):
     _fields_ = [("ngpu", C.c_int32), ("device_ids", C.POINTER(C.c_int32)), ("verbose", C.c_int32),
                 ("inputs_on_device", C.c_int32), ("unit_first", C.c_int64), ("unit_stride", C.c_int64),
                 ("unit_count", C.c_int64), ("batch", C.c_int32), ("steal_chunk", C.c_int32),
-                ("use_nccl", C.c_int32), ("reserved", C.c_int32 * 5)]
+                ("use_nccl", C.c_int32), ("df_block", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 class Stats(C.Structure):
@@ -53,6 +53,13 @@ class Stats(C.Structure):
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+
+
+class DfPlanInfo(C.Structure):
+    _fields_ = [("npanel", C.c_int32), ("block", C.c_int32), ("panel_mode", C.c_int32), ("flat", C.c_int32),
+                ("bytes_panels", C.c_double), ("bytes_b", C.c_double), ("bytes_gv", C.c_double), ("bytes_t2", C.c_double),
+                ("bytes_factors", C.c_double), ("bytes_w_workspace", C.c_double), ("bytes_total", C.c_double),
+                ("build_flop_fraction", C.c_double)]
 
 
 class UniqueId(C.Structure):
@@ -69,10 +76,12 @@ class MpqcTError(RuntimeError):
 SYMBOLS = [
     "mpqc_t_energy", "mpqc_t_energy_df", "mpqc_t_create", "mpqc_t_upload", "mpqc_t_upload_df", "mpqc_t_run", "mpqc_t_debug_w", "mpqc_t_stream",
     "mpqc_t_comm_unique_id", "mpqc_t_comm_create_rank", "mpqc_t_comm_create_local", "mpqc_t_comm_size", "mpqc_t_comm_destroy",
-    "mpqc_t_energy_comm", "mpqc_t_energy_df_comm", "mpqc_t_host_alloc", "mpqc_t_host_free", "mpqc_t_run_vblocks", "mpqc_t_run_comm",
+    "mpqc_t_energy_comm", "mpqc_t_energy_df_comm", "mpqc_t_host_alloc", "mpqc_t_host_free", "mpqc_t_run_vblocks", "mpqc_t_run_comm", "mpqc_t_set_df_block", "mpqc_t_plan_df", "mpqc_t_query",
     "mpqc_t_destroy", "mpqc_t_triple_count", "mpqc_t_triple_of_unit", "mpqc_t_flops", "mpqc_t_unit_flops",
     "mpqc_t_device_count", "mpqc_t_plan", "mpqc_t_version", "mpqc_t_strerror", "mpqc_t_last_error", "mpqc_t_microbench",
 ]
+
+QUERY_PANEL_SLOTS, QUERY_PANEL_MODE, QUERY_FLAT, QUERY_PANELS_BUILT, QUERY_PANEL_BLOCK = range(5)
 
 _lib = None
 
@@ -107,6 +116,12 @@ def load() -> C.CDLL:
     lib.mpqc_t_run_comm.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int32, c_double_p, c_double_p,
                                     C.POINTER(Stats)]
     lib.mpqc_t_run_comm.restype = C.c_int
+    lib.mpqc_t_query.argtypes = [vp, C.c_int32, C.POINTER(C.c_int64)]
+    lib.mpqc_t_query.restype = C.c_int
+    lib.mpqc_t_set_df_block.argtypes = [vp, C.c_int32]
+    lib.mpqc_t_set_df_block.restype = C.c_int
+    lib.mpqc_t_plan_df.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.POINTER(DfPlanInfo)]
+    lib.mpqc_t_plan_df.restype = C.c_int
     lib.mpqc_t_comm_unique_id.argtypes = [C.POINTER(UniqueId)]
     lib.mpqc_t_comm_unique_id.restype = C.c_int
     lib.mpqc_t_comm_create_rank.argtypes = [C.POINTER(vp), C.c_int32, C.c_int32, C.POINTER(UniqueId), C.c_int32]

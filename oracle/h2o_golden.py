@@ -300,9 +300,9 @@ def eri_3c(fP, f1, f2):
 # ---------------------------------------------------------------------------------------------------------
 # RI-RHF, DF-CCSD
 # ---------------------------------------------------------------------------------------------------------
-def integrals():
+def integrals(obs_table=None):
     geom = [(s, np.array(xyz) / BOHR) for s, xyz in GEOM]
-    obs, To = build_basis(B631G, geom)
+    obs, To = build_basis(B631G if obs_table is None else obs_table, geom, pure_d=True)
     aux, Ta = build_basis(CCPVDZ, geom, pure_d=True)
     n, na = len(obs), len(aux)
     S = np.zeros((n, n)); T = np.zeros((n, n)); V = np.zeros((n, n))
@@ -323,9 +323,12 @@ def integrals():
         for i in range(n):
             for j in range(i + 1):
                 J3[p, i, j] = J3[p, j, i] = eri_3c(aux[p], obs[i], obs[j])
-    # cartesian -> final bases
+    # cartesian -> final bases (the orbital-basis transform is the identity for 6-31G; for cc-pVDZ it takes the six
+    # cartesian d functions to the five solid harmonics -- any invertible mixing inside a shell leaves energies unchanged)
     J2 = Ta @ J2 @ Ta.T
     J3 = np.einsum("Pp,pij->Pij", Ta, J3)
+    S, T, V = To @ S @ To.T, To @ T @ To.T, To @ V @ To.T
+    J3 = np.einsum("im,jn,Pmn->Pij", To, To, J3, optimize=True)
     enuc = sum(Z[a[0]] * Z[b[0]] / np.linalg.norm(a[1] - b[1]) for ia, a in enumerate(geom) for b in geom[:ia])
     return S, T + V, J2, J3, enuc
 
@@ -472,14 +475,20 @@ def ccsd_spinorbital(B, C, eps, nocc, nfrozen, tol=1e-13, maxit=300):
     return dict(e_mp2=e_mp2, e_ccsd=e, t1=t1_cs, t2=t2_cs, iterations=it + 1, no=no, nv=nv, Bmo=Bmo)
 
 
-def main(write=True):
-    S, H, J2, J3, enuc = integrals()
+def main(write=True, obs="631g"):
+    """obs = "631g": the reference's validation case (OBS 6-31G, DFBS cc-pVDZ), compared with its stored output.
+    obs = "ccpvdz": BASELINE.json configs[0], H2O CCSD(T)/cc-pVDZ (OBS = DFBS = cc-pVDZ, frozen core: o = 4, v = 19);
+    the reference stores no output for it, so this only produces real-molecule tensors at that shape
+    (tests/golden/h2o_ccpvdz.npz) on which the oracle restatements and the CUDA path must agree."""
+    have_ref = obs == "631g"
+    ref = REF if have_ref else dict(scf=float("nan"), mp2=float("nan"), ccsd=float("nan"), t=float("nan"), total=float("nan"))
+    S, H, J2, J3, enuc = integrals(B631G if have_ref else CCPVDZ)
     nocc, nfrozen = 5, 1                      # H2O: 10 electrons; frozen core = O 1s (molecule.cpp:190-208)
     e_scf, C, eps, B = rhf_df(S, H, J2, J3, enuc, nocc)
-    print(f"SCF   {e_scf:.13f}   reference {REF['scf']:.13f}   diff {e_scf - REF['scf']:+.2e}")
+    print(f"SCF   {e_scf:.13f}   reference {ref['scf']:.13f}   diff {e_scf - ref['scf']:+.2e}")
     cc = ccsd_spinorbital(B, C, eps, nocc, nfrozen)
-    print(f"MP2   {cc['e_mp2']:.15f}   reference {REF['mp2']:.15f}   diff {cc['e_mp2'] - REF['mp2']:+.2e}")
-    print(f"CCSD  {cc['e_ccsd']:.15f}   reference {REF['ccsd']:.15f}   diff {cc['e_ccsd'] - REF['ccsd']:+.2e}"
+    print(f"MP2   {cc['e_mp2']:.15f}   reference {ref['mp2']:.15f}   diff {cc['e_mp2'] - ref['mp2']:+.2e}")
+    print(f"CCSD  {cc['e_ccsd']:.15f}   reference {ref['ccsd']:.15f}   diff {cc['e_ccsd'] - ref['ccsd']:+.2e}"
           f"   ({cc['iterations']} iterations)")
     no, nv, Bmo = cc["no"], cc["nv"], cc["Bmo"]
     Boo, Bov, Bvv = Bmo[:, :no, :no], Bmo[:, :no, no:], Bmo[:, no:, no:]
@@ -493,17 +502,20 @@ def main(write=True):
             np.ascontiguousarray(g_abci), eps_occ, eps_vir)
     e_t = {"straight": oc.straight(*args), "coarse": oc.coarse(*args, vir_block=4), "ijk": oc.ijk_driven(*args)}
     for k, val in e_t.items():
-        print(f"(T) {k:9s} {val:.18f}   reference {REF['t']:.18f}   diff {val - REF['t']:+.2e}")
+        print(f"(T) {k:9s} {val:.18f}   reference {ref['t']:.18f}   diff {val - ref['t']:+.2e}")
     total = e_scf + cc["e_ccsd"] + e_t["straight"]
-    print(f"total {total:.13f}   reference {REF['total']:.13f}   diff {total - REF['total']:+.2e}")
+    print(f"total {total:.13f}   reference {ref['total']:.13f}   diff {total - ref['total']:+.2e}")
     if write:
-        out = os.path.join(ROOT, "tests", "golden", "h2o_631g.npz")
+        out = os.path.join(ROOT, "tests", "golden", "h2o_631g.npz" if have_ref else "h2o_ccpvdz.npz")
+        extra = dict(ref_scf=REF["scf"], ref_mp2=REF["mp2"], ref_ccsd=REF["ccsd"], ref_t=REF["t"], ref_total=REF["total"]) \
+            if have_ref else dict(x_ab=np.ascontiguousarray(Bvv), x_ij=np.ascontiguousarray(Boo),
+                                  x_ai=np.ascontiguousarray(Bov.transpose(0, 2, 1)))
         np.savez(out, eps=eps, n_frozen=nfrozen, n_occ=nocc, t1=args[0], t2=args[1], g_abij=args[2], g_aijk=args[3],
                  g_abci=args[4], e_scf=e_scf, e_mp2=cc["e_mp2"], e_ccsd=cc["e_ccsd"], e_t_oracle=e_t["straight"],
-                 ref_scf=REF["scf"], ref_mp2=REF["mp2"], ref_ccsd=REF["ccsd"], ref_t=REF["t"], ref_total=REF["total"])
+                 e_t_coarse=e_t["coarse"], e_t_ijk=e_t["ijk"], **extra)
         print("wrote", out)
     return e_scf, cc, e_t
 
 
 if __name__ == "__main__":
-    main()
+    main(obs="ccpvdz" if "--ccpvdz" in sys.argv else "631g")

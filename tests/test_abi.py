@@ -175,3 +175,21 @@ def test_tiling_plan_of_the_baseline_configs(lib):
         assert info.kp % 8 == 0 and info.kp >= v + o and info.flop_efficiency > lo, (o, v, info.flop_efficiency)
     bad = L.PlanInfo()
     assert lib.mpqc_t_plan(0, 5, 1, C.byref(bad)) == L.ERR_BAD_ARG
+
+
+def test_density_fitted_memory_model(lib):
+    # host-only model of the density-fitted path: with a panel cache the v^3 o operand is never
+    # resident, which moves the single-GPU memory ceiling
+    def plan(o, v, naux, block, flat=0):
+        info = L.DfPlanInfo()
+        assert lib.mpqc_t_plan_df(o, v, naux, block, flat, C.byref(info)) == L.OK
+        return info
+    res = plan(40, 530, 1140, 0)                 # (H2O)10 / cc-pVTZ, everything resident: 52 GB of panels alone
+    assert not res.panel_mode and res.npanel == 40 and 51e9 < res.bytes_panels < 53e9
+    pc = plan(40, 530, 1140, 6)                  # panel cache, occupied block 6: 18 panels
+    assert pc.panel_mode and pc.npanel == 18 and pc.block == 6
+    assert pc.bytes_total < 60e9 and pc.build_flop_fraction < 0.02
+    big = plan(40, 1000, 3500, 3)                # v = 1000 on ONE GPU: A alone would be 333 GB
+    assert big.panel_mode and big.bytes_total < 170e9 and big.build_flop_fraction < 0.08
+    assert plan(40, 1000, 3500, 0).bytes_total > 333e9
+    assert lib.mpqc_t_plan_df(0, 5, 5, 0, 0, C.byref(L.DfPlanInfo())) == L.ERR_BAD_ARG

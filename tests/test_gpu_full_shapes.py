@@ -136,3 +136,39 @@ def test_full_shape_density_fitted_flat_mode(lib, name):
         del os.environ["MPQC_T_FLAT"]
         lib.mpqc_t_destroy(h)
     assert worst < TOL, worst
+
+
+def test_water10_panel_cache_fits_in_60_gb(lib):
+    # (H2O)10 / cc-pVTZ shape with the density-fitted hand-off in panel-cache mode (occupied block 6 -> 18 operand panels,
+    # row patches): the v^3 o operand (52 GB as A, 104 GB with its transposed copy) is never resident and the whole
+    # problem holds < 60 GB of HBM; sampled units against the oracle.
+    o, v, seed = SHAPES["water10-cc-pVTZ"]
+    pd = make_problem_torch(o, v, "cuda", seed=seed, dense_abci=False)
+    torch.cuda.synchronize()
+    dfp = L.make_df_problem(o, v, int(pd["naux"]), pd["eps_occ"], pd["eps_vir"], pd["t1"], pd["t2"], pd["x_ab"],
+                            pd["x_ij"], pd["x_ai"])
+    free0 = torch.cuda.mem_get_info()[0]
+    os.environ["MPQC_T_FLAT"] = "0"
+    h = C.c_void_p()
+    try:
+        L.check(lib.mpqc_t_create(C.byref(h), o, v, 0), "create")
+        L.check(lib.mpqc_t_set_df_block(h, 6), "set_df_block")
+        L.check(lib.mpqc_t_upload_df(h, C.byref(dfp), 1, None), "upload_df")
+        n = lib.mpqc_t_triple_count(o)
+        args = _oracle_args(pd, LazyAbci(pd["x_ab"], pd["x_ai"]))
+        worst = _check_units(lib, h, o, args, [3, n - 5])
+        # a contiguous run of units through the cache (several block triples): compare its sum with the same units one by one
+        e, st = C.c_double(), L.Stats()
+        L.check(lib.mpqc_t_run(h, n // 2, 1, 40, 0, C.byref(e), None, C.byref(st)), "run")
+        used = free0 - torch.cuda.mem_get_info()[0]
+        q = C.c_int64()
+        L.check(lib.mpqc_t_query(h, L.QUERY_PANEL_SLOTS, C.byref(q)), "query")
+    finally:
+        del os.environ["MPQC_T_FLAT"]
+        lib.mpqc_t_destroy(h)
+    assert worst < TOL, worst
+    assert q.value == 18 and st.units == 40
+    assert used < 60e9, used
+    info = L.DfPlanInfo()
+    L.check(lib.mpqc_t_plan_df(o, v, int(pd["naux"]), 6, 0, C.byref(info)), "plan_df")
+    assert info.bytes_total < 60e9 and abs(info.bytes_total - used) < 0.15 * used

@@ -143,6 +143,45 @@ def test_h2o_reference_golden():
     assert abs(float(g["e_ccsd"]) - float(g["ref_ccsd"])) < 1e-9      # reference converged CCSD to 1e-9 (:313)
 
 
+REF_T_LAPLACE = -0.000868503092063519    # outputs/h2o-ccsd_t-lt-631g-pvdz.out:377 (approach "laplace", 3 quadrature points)
+
+
+def test_exact_t_differs_from_the_stored_laplace_value():
+    # the Laplace-transform (T) is an approximate method (out of scope here): the reference stores BOTH numbers for the
+    # same molecule, they differ by 8.93e-8 Eh -- 90x the 1e-9 acceptance tolerance -- so an implementation that
+    # accidentally reproduced the approximate method would be caught.  The exact sum must sit on the exact value.
+    g, args = _h2o_args()
+    e = oc.ijk_driven(*args)
+    assert abs(REF_T - REF_T_LAPLACE - 8.9285e-8) < 1e-11
+    assert abs((e - REF_T_LAPLACE) - 8.9285e-8) < 1e-9
+    assert abs(e - REF_T) < 1e-11 < abs(e - REF_T_LAPLACE)
+
+
+H2O_DZ = os.path.join(os.path.dirname(__file__), "golden", "h2o_ccpvdz.npz")
+
+
+def test_h2o_ccpvdz_fixture():
+    # BASELINE.json configs[0]: H2O CCSD(T)/cc-pVDZ, frozen core -> o = 4, v = 19 (oracle/h2o_golden.py --ccpvdz: own
+    # integrals, DF-RHF, DF-CCSD with OBS = DFBS = cc-pVDZ).  The reference stores no output for this input, so this
+    # fixture pins the restatements against each other (and the CUDA path against them) on real-molecule tensors of
+    # that shape; the reference-produced pin is the 6-31G case above.
+    g = np.load(H2O_DZ)
+    nf, no = int(g["n_frozen"]), int(g["n_occ"])
+    assert g["t1"].shape == (19, 4) and g["g_abci"].shape == (19, 19, 19, 4) and len(g["eps"]) == 24
+    args = tuple(np.ascontiguousarray(g[k]) for k in ("t1", "t2", "g_abij", "g_aijk", "g_abci")) + \
+        (g["eps"][nf:no].copy(), g["eps"][no:].copy())
+    es = [oc.straight(*args), oc.coarse(*args, vir_block=8), oc.coarse(*args, vir_block=5), oc.ijk_driven(*args),
+          straight_c(args[0], args[1], args[2], args[3], args[4], g["eps"], nf, 0)]
+    for e in es:
+        assert abs(e - float(g["e_t_oracle"])) < 1e-13, e
+    assert -4e-3 < es[0] < -3e-3 and -0.21 < float(g["e_ccsd"]) < -0.20      # a sane water/cc-pVDZ correlation energy
+    # the density-fitting factors stored with it reproduce the integral classes (the DF hand-off of the C ABI)
+    xab, xij, xai = g["x_ab"], g["x_ij"], g["x_ai"]
+    np.testing.assert_allclose(np.einsum("Kbi,Kac->abci", xai, xab), g["g_abci"], atol=1e-13)
+    np.testing.assert_allclose(np.einsum("Kai,Kbj->abij", xai, xai), g["g_abij"], atol=1e-13)
+    np.testing.assert_allclose(np.einsum("Kik,Kaj->aijk", xij, xai), g["g_aijk"], atol=1e-13)
+
+
 def test_h2o_fixture_is_reproducible():
     # regenerate the tensors from scratch (integrals -> DF-RHF -> DF-CCSD) and compare with the committed fixture
     from oracle import h2o_golden
