@@ -187,6 +187,11 @@ int mpqc_t_run_comm(mpqc_t_handle* h, mpqc_t_comm* c, int64_t first, int64_t str
  * the whole-job result can be checked against sampled iterations of the reference algorithm. */
 int mpqc_t_run_vblocks(mpqc_t_handle* h, int64_t first, int64_t stride, int64_t count, int32_t batch,
                        double* partial_e, double* unit_e, double* vblock_e, mpqc_t_stats* stats);
+/* The W build alone, batched: W^{abc}_{ijk} (the six particle + six hole contractions, ccsd_t.h:1142-1146) for n
+ * ARBITRARY occupied triples (no ordering required), written as dense [n][v][v][v] arrays (a,b,c row-major) into device
+ * memory of the handle's device (out_on_device = 1) or host memory.  This is the entry point an iterative-triples
+ * model (CC3 / CCSDT-1, cc3.h:55+, ccsdt1.h:55+: the same contraction shapes every CC iteration) would call. */
+int mpqc_t_w_batch(mpqc_t_handle* h, const int32_t* triples /* [n][3] */, int64_t n, double* w_out, int32_t out_on_device);
 /* debugging / parity aid: W^{abc}_{ijk} of one occupied triple as a dense [v][v][v] host array */
 int mpqc_t_debug_w(mpqc_t_handle* h, int32_t i, int32_t j, int32_t k, double* w_host);
 /* what the last upload decided for this handle */

@@ -343,8 +343,33 @@ class CCSD_T:
         return self.triples_energy_
 
 
-#: the KeyVal registry entry of the drop-in (keyval.h:129-139 asserts one registration per key)
-REGISTRY = {"CCSD(T)": CCSD_T}
+class CCSD_T_F12(CCSD_T):
+    """Mirror of the path's SECOND caller, ``CCSD_T_F12<Tile>::evaluate`` (f12/ccsd_t_f12.h:47-69): it computes the
+    CCSD(F12) energy first (out of scope here: supplied by the provider), purges the integral registries, and then calls
+    the protected, non-virtual ``CCSD_T::compute_ccsd_t()`` of its base and adds ``triples_energy()``.  Because the GPU
+    path is dispatched INSIDE ``compute_ccsd_t`` (integration/mpqc_ccsd_t_gpu.patch), this caller gets it unchanged."""
+
+    def __init__(self, kv: dict, ccsd=None, out=None, comm=None, reduce=None):
+        kv = dict(kv or {})
+        t = kv.pop("type", "CCSD(T)F12")
+        if t != "CCSD(T)F12":
+            raise InputError(f"CCSD_T_F12 constructed from a KeyVal of type {t!r}", "type", t)
+        super().__init__(dict(kv, type="CCSD(T)"), ccsd=ccsd, out=out, comm=comm, reduce=reduce)
+
+    def evaluate(self, result: Energy):                                           # f12/ccsd_t_f12.h:47-69
+        if not self.computed_:
+            cc = self._ccsd
+            ccsd_f12_energy = float(cc.ccsd_f12_energy() if hasattr(cc, "ccsd_f12_energy") else cc.ccsd_energy())
+            t0 = time.perf_counter()
+            self.compute_ccsd_t()                                                 # :59
+            print(f"(T) Time in CCSD(T)F12:  {time.perf_counter() - t0}", file=self._out)
+            self.computed_ = True
+            result.value = ccsd_f12_energy + self.triples_energy()                # :67
+        return result
+
+
+#: the KeyVal registry entries of the drop-in (keyval.h:129-139 asserts one registration per key)
+REGISTRY = {"CCSD(T)": CCSD_T, "CCSD(T)F12": CCSD_T_F12}
 
 
 def class_ptr(kv: dict, **deps):

@@ -1411,6 +1411,43 @@ int mpqc_t_debug_w(mpqc_t_handle* h, int32_t i, int32_t j, int32_t k, double* w_
   return MPQC_T_OK;
 }
 
+int mpqc_t_w_batch(mpqc_t_handle* h, const int32_t* triples, int64_t n, double* w_out, int32_t out_on_device) {
+  MPQC_T_CHECK(h && triples && w_out, MPQC_T_ERR_BAD_ARG, "NULL argument");
+  MPQC_T_CHECK(h->uploaded, MPQC_T_ERR_BAD_ARG, "mpqc_t_upload has not been called on this handle");
+  MPQC_T_CHECK(n >= 0, MPQC_T_ERR_BAD_ARG, "n < 0");
+  for (int64_t q = 0; q < 3 * n; ++q)
+    MPQC_T_CHECK(triples[q] >= 0 && triples[q] < h->o, MPQC_T_ERR_BAD_ARG, "occupied index out of range");
+  if (n == 0) return MPQC_T_OK;
+  MPQC_T_CUDA(cudaSetDevice(h->device));
+  const int64_t v = h->v, v3 = v * v * v;
+  int batch = (int)std::min<int64_t>(std::max(1, auto_batch(h)), n);
+  if (h->panel_mode) batch = std::min(batch, std::max(1, h->npanel / 3));   // a batch never needs more panels than the pool holds
+  MPQC_T_TRY(ensure_work(h, batch));
+  MPQC_T_TRY(ensure_units(h, n));
+  MPQC_T_CUDA(cudaMemcpyAsync(h->triples_dev, triples, (size_t)n * 3 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  DevBuf stage;                       // host output: assembled on the device batch by batch, then copied back
+  if (!out_on_device) MPQC_T_TRY(stage.alloc((size_t)batch * v3));
+  for (int64_t off = 0; off < n; off += batch) {
+    const int nb = (int)std::min<int64_t>(batch, n - off);
+    if (h->panel_mode) {
+      std::vector<int> need(triples + 3 * off, triples + 3 * (off + nb));
+      std::sort(need.begin(), need.end());
+      need.erase(std::unique(need.begin(), need.end()), need.end());
+      MPQC_T_TRY(ensure_panels(h, need, nullptr));
+    }
+    MPQC_T_TRY(launch_gemm(h, nb, h->triples_dev + 3 * off));
+    double* dst = out_on_device ? w_out + off * v3 : stage.p;
+    w_assemble_kernel<<<dim3((unsigned)(h->ntile * h->ntile * h->ntile), (unsigned)nb), 512, 0, h->stream>>>(h->W, dst, (int)v,
+                                                                                                         h->ldw, h->ntile);
+    MPQC_T_CUDA(cudaGetLastError());
+    if (!out_on_device)
+      MPQC_T_CUDA(cudaMemcpyAsync(w_out + off * v3, stage.p, (size_t)nb * v3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
+  MPQC_T_CUDA(cudaStreamSynchronize(h->stream));
+  MPQC_T_CUDA(cudaGetLastError());
+  return MPQC_T_OK;
+}
+
 }  // extern "C"
 
 namespace {

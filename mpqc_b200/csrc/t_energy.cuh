@@ -239,4 +239,33 @@ t_energy_vblock_kernel(const double* __restrict__ partial, int ntt, int nbatch, 
   vblock_e[tt] += s;
 }
 
+// W^{abc}_{ijk} itself as a dense [v][v][v] array (mpqc_t_w_batch: the hook iterative-triples models such as CC3 /
+// CCSDT-1 would call every iteration, cc3.h:55+, ccsdt1.h:55+):  W[a][b][c] = N_0[a][b][c] + N_1[a][c][b] + N_2[c][b][a].
+// One 512-thread block per 8x8x8 output tile: the three source tiles (at permuted tile coordinates) are read with
+// 64-byte row segments into shared memory and the permuted adds happen there, so every global access is a row.
+__global__ void __launch_bounds__(512)
+w_assemble_kernel(const double* __restrict__ n_all, double* __restrict__ w_out, int v, int ldw, int ntile) {
+  __shared__ double s[3][8][8][9];
+  const int b = blockIdx.y;
+  int t = blockIdx.x;
+  const int TC = t % ntile;
+  t /= ntile;
+  const int TB = t % ntile, TA = t / ntile;
+  const int64_t nstride = (int64_t)v * v * ldw;
+  const double* n0 = n_all + (int64_t)b * 3 * nstride;
+  const int x = threadIdx.x >> 6, y = (threadIdx.x >> 3) & 7, z = threadIdx.x & 7;
+  // tile (X,Y,Z) of an array: element (x,y,z) at [(X*8+x)*v + (Y*8+y)]*ldw + Z*8+z
+  auto fetch = [&](const double* base, int X, int Y, int Z) -> double {
+    const int g0 = X * 8 + x, g1 = Y * 8 + y, g2 = Z * 8 + z;
+    return (g0 < v && g1 < v && g2 < v) ? __ldg(base + ((int64_t)g0 * v + g1) * ldw + g2) : 0.0;
+  };
+  s[0][x][y][z] = fetch(n0, TA, TB, TC);                  // N_0[a][b][c]
+  s[1][x][y][z] = fetch(n0 + nstride, TA, TC, TB);        // N_1[a][c][b]   (x,y,z) = (a,c,b)
+  s[2][x][y][z] = fetch(n0 + 2 * nstride, TC, TB, TA);    // N_2[c][b][a]   (x,y,z) = (c,b,a)
+  __syncthreads();
+  const int a = TA * 8 + x, bb = TB * 8 + y, c = TC * 8 + z;
+  if (a < v && bb < v && c < v)
+    w_out[(int64_t)b * v * v * v + ((int64_t)a * v + bb) * v + c] = s[0][x][y][z] + s[1][x][z][y] + s[2][z][y][x];
+}
+
 }  // namespace mpqc_t

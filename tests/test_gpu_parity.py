@@ -15,7 +15,7 @@ import pytest
 import torch
 
 from mpqc_b200 import lib as L
-from mpqc_b200.ccsd_t import CCSD_T, DenseCCSD, Energy
+from mpqc_b200.ccsd_t import CCSD_T, CCSD_T_F12, DenseCCSD, Energy
 from mpqc_b200.synthetic import make_problem, make_problem_torch
 from oracle import ccsd_t_oracle as oc
 
@@ -257,6 +257,30 @@ def test_local_communicator_replicates_inputs_over_nvlink(lib, df):
         lib.mpqc_t_comm_destroy(comm)
 
 
+def test_w_batch_hook_for_iterative_triples(lib):
+    # mpqc_t_w_batch: W for a batch of ARBITRARY (unordered, repeated) occupied triples, dense [n][v][v][v], to host
+    # and to device memory -- the call a CC3 / CCSDT-1 iteration would make
+    o, v = 5, 37
+    p = make_problem(o, v, seed=23)
+    h = Handle(lib, p)
+    tri = np.array([[0, 3, 1], [4, 4, 2], [2, 0, 0], [1, 1, 1], [3, 4, 0], [0, 3, 1]], dtype=np.int32)
+    n = len(tri)
+    w_host = np.zeros((n, v, v, v))
+    L.check(lib.mpqc_t_w_batch(h.h, tri.ctypes.data_as(C.POINTER(C.c_int32)), n, w_host.ctypes.data, 0), "w_batch")
+    w_dev = torch.zeros((n, v, v, v), dtype=torch.float64, device="cuda")
+    L.check(lib.mpqc_t_w_batch(h.h, tri.ctypes.data_as(C.POINTER(C.c_int32)), n, w_dev.data_ptr(), 1), "w_batch")
+    torch.cuda.synchronize()
+    for q, (i, j, k) in enumerate(tri):
+        w_ref = oc.w_ijk(p["t2"], p["g_aijk"], p["g_abci"], int(i), int(j), int(k))
+        np.testing.assert_allclose(w_host[q], w_ref, atol=1e-13 * max(1.0, np.abs(w_ref).max()))
+        np.testing.assert_array_equal(w_dev[q].cpu().numpy(), w_host[q])
+    np.testing.assert_array_equal(w_host[0], w_host[5])
+    np.testing.assert_array_equal(h.w(0, 3, 1), w_host[0])
+    bad = np.array([[0, 5, 1]], dtype=np.int32)
+    assert lib.mpqc_t_w_batch(h.h, bad.ctypes.data_as(C.POINTER(C.c_int32)), 1, w_host.ctypes.data, 0) == L.ERR_BAD_ARG
+    h.close()
+
+
 def test_sharding_and_batching_are_bitwise_consistent(lib):
     # any unit sharding / batch size gives bit-identical per-unit energies, so 1/2/4/8-GPU sums agree
     p = make_problem(6, 27, seed=9)
@@ -295,6 +319,20 @@ def test_plugin_interface_end_to_end(lib):
     assert "(T) Energy:" in out.getvalue() and "(T) Time in CCSD(T):" in out.getvalue()
     wfn.obsolete()
     assert wfn.triples_energy() == 0.0
+
+
+def test_second_caller_gets_the_gpu_path(lib):
+    # CCSD(T)F12 (f12/ccsd_t_f12.h:47-69): CCSD(F12) energy from its own code, then the base's compute_ccsd_t()
+    p = make_problem(4, 15, seed=6)
+    cc = DenseCCSD.from_problem(p, n_frozen=1, e_ccsd=-0.25)
+    cc.ccsd_f12_energy = lambda: -0.31
+    out = io.StringIO()
+    wfn = CCSD_T_F12({"type": "CCSD(T)F12"}, ccsd=cc, out=out)
+    res = wfn.evaluate(Energy())
+    e_ref = oc.ijk_driven(*_args(p))
+    assert abs(wfn.triples_energy() - e_ref) < TOL and abs(res.value - (-0.31 + e_ref)) < TOL
+    assert "(T) Energy:" in out.getvalue() and "(T) Time in CCSD(T)F12:" in out.getvalue()
+    assert wfn.stats()["kernel_launches"] > 0
 
 
 def test_relabeling_invariance_property(lib):

@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from mpqc_b200.ccsd_t import (CCSD_T, DenseCCSD, Energy, FeatureDisabled, InputError, TRange1Engine, class_ptr)
+from mpqc_b200.ccsd_t import (CCSD_T, CCSD_T_F12, DenseCCSD, Energy, FeatureDisabled, InputError, TRange1Engine, class_ptr)
 from mpqc_b200.synthetic import make_problem
 from oracle import ccsd_t_oracle as oc
 
@@ -36,6 +36,15 @@ def test_invalid_approach_raises_input_error():
     with pytest.raises(InputError):
         CCSD_T({"rank": 2, "world_size": 2})
     assert isinstance(class_ptr({"type": "CCSD(T)"}), CCSD_T)
+
+
+def test_second_caller_is_registered_and_shares_the_dispatcher():
+    # "CCSD(T)F12" (f12/ccsd_t_f12.h:47-69) is the path's second caller: same keywords, same compute_ccsd_t()
+    w = class_ptr({"type": "CCSD(T)F12", "approach": "coarse", "reblock_occ": 4})
+    assert isinstance(w, CCSD_T_F12) and isinstance(w, CCSD_T) and w.approach_ == "coarse" and w.reblock_
+    assert CCSD_T_F12.compute_ccsd_t is CCSD_T.compute_ccsd_t          # not overridden: the base's dispatcher runs
+    with pytest.raises(InputError):
+        CCSD_T_F12({"type": "CCSD(T)"})
 
 
 def test_laplace_is_feature_disabled():
