@@ -459,6 +459,7 @@ def run_ours(args):
                 L.check(lib.mpqc_t_comm_create_local(C.byref(lc), world, None), "mpqc_t_comm_create_local")
                 setup_s = time.perf_counter() - t0
                 walls = []
+                opt.verbose = 2 if os.environ.get("MPQC_T_BENCH_VERBOSE") else 0
                 for _rep in range(2):
                     ist, ie = L.Stats(), C.c_double()
                     t0 = time.perf_counter()

@@ -45,6 +45,12 @@ for (o, v) in [(9, 41), (12, 70)]:
     L.check(lib.mpqc_t_energy_comm(comm, C.byref(prob), C.byref(opt), C.byref(e), C.byref(st)), "energy_comm")
     ed, sd = C.c_double(), L.Stats()
     L.check(lib.mpqc_t_energy_df_comm(comm, C.byref(dfp), C.byref(opt), C.byref(ed), C.byref(sd)), "energy_df_comm")
+    # density-fitted hand-off with the operand panel cache (occupied block 2): groups of units, not single units, are
+    # dealt to the ranks
+    opt_p = L.Options()
+    opt_p.unit_count, opt_p.df_block = -1, 2
+    ep, sp = C.c_double(), L.Stats()
+    L.check(lib.mpqc_t_energy_df_comm(comm, C.byref(dfp), C.byref(opt_p), C.byref(ep), C.byref(sp)), "energy_df_comm(panels)")
     # single-GPU plain call on this rank's device
     o1 = L.Options()
     ids = (C.c_int32 * 1)(local)
@@ -62,6 +68,9 @@ for (o, v) in [(9, 41), (12, 70)]:
     lib.mpqc_t_destroy(h)
     e_ref = oc.ijk_driven(p["t1"], p["t2"], p["g_abij"], p["g_aijk"], p["g_abci"], p["eps_occ"], p["eps_vir"])
     allv = [torch.zeros(3, dtype=torch.float64) for _ in range(world)]
+    units_panel = torch.tensor([float(sp.units)], dtype=torch.float64)
+    dist.all_reduce(units_panel)
+    assert int(units_panel[0]) == n, (int(units_panel[0]), n)      # every unit ran exactly once across the ranks
     dist.all_gather(allv, torch.tensor([e.value, ed.value, er.value], dtype=torch.float64))
     same = all(bool(torch.equal(x, allv[0])) for x in allv)
     h2d = torch.tensor([float(st.bytes_h2d)], dtype=torch.float64)
@@ -70,9 +79,11 @@ for (o, v) in [(9, 41), (12, 70)]:
     rec = {"o": o, "v": v, "e_comm": e.value, "e_single": e1.value, "e_df_comm": ed.value, "e_run_comm": er.value,
            "oracle": e_ref, "identical_on_all_ranks": same, "bitwise_equal_single_gpu": e.value == e1.value == er.value,
            "abs_diff_oracle": abs(e.value - e_ref), "abs_diff_df": abs(ed.value - e.value),
+           "e_df_panels_comm": ep.value, "abs_diff_df_panels": abs(ep.value - e.value),
+           "panel_units_this_rank": int(sp.units), "panel_units_all_ranks": int(units_panel[0]),
            "units_this_rank": int(st.units), "h2d_bytes_all_ranks": float(h2d[0]), "dense_input_bytes": dense_bytes}
     assert same and rec["bitwise_equal_single_gpu"], rec
-    assert rec["abs_diff_oracle"] < 1e-10 and rec["abs_diff_df"] < 1e-12, rec
+    assert rec["abs_diff_oracle"] < 1e-10 and rec["abs_diff_df"] < 1e-12 and rec["abs_diff_df_panels"] < 1e-12, rec
     assert st.units in (n // world, n // world + 1), rec
     assert rec["h2d_bytes_all_ranks"] < 1.25 * dense_bytes + world * (1 << 16) + 24 * n * world, rec
     out[f"o{o}_v{v}"] = rec
