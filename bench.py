@@ -452,6 +452,7 @@ def run_ours(args):
 
         # ---- the library's own one-process / N-threads path on all N GPUs (rank 0; the other ranks idle) -------
         if world > 1 and not args.no_in_process:
+            lib.mpqc_t_comm_release_cache(comm)             # the rank-mode communicator's cached operand memory
             host_barrier()                                  # everyone's device memory is free again
             if rank == 0:
                 lc = C.c_void_p()

@@ -150,6 +150,9 @@ int mpqc_t_comm_unique_id(mpqc_t_unique_id* id);
 int mpqc_t_comm_create_rank(mpqc_t_comm** c, int32_t nranks, int32_t rank, const mpqc_t_unique_id* id, int32_t device);
 int mpqc_t_comm_create_local(mpqc_t_comm** c, int32_t ngpu, const int32_t* device_ids /* NULL -> 0..ngpu-1 */);
 int mpqc_t_comm_size(const mpqc_t_comm* c);
+/* The communicator keeps the device memory of the last problem (operand panels, workspaces) for the next call with the
+ * same (o, v) -- allocating and freeing tens of GB costs seconds on some hosts; this hands it back to the driver now. */
+int mpqc_t_comm_release_cache(mpqc_t_comm* c);
 int mpqc_t_comm_destroy(mpqc_t_comm* c);
 int mpqc_t_energy_comm(mpqc_t_comm* c, const mpqc_t_problem* p, const mpqc_t_options* opt, double* e_t, mpqc_t_stats* stats);
 int mpqc_t_energy_df_comm(mpqc_t_comm* c, const mpqc_t_df_problem* p, const mpqc_t_options* opt, double* e_t,

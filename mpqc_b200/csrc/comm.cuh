@@ -87,8 +87,14 @@ struct CommMember {
 
 }  // namespace mpqc_t
 
+struct mpqc_t_handle;
+
 struct mpqc_t_comm {
   int nranks = 1;
   bool local = false;                          // true: all nranks members live in this process (one thread per GPU)
   std::vector<mpqc_t::CommMember> members;     // local: nranks entries; rank mode: one
+  // Device memory of the last problem, kept per member between calls: allocating and freeing the ~40 GB of operand
+  // panels costs seconds per call on some hosts, and a geometry optimisation calls (T) again with the same (o, v).
+  // Released by mpqc_t_comm_release_cache / mpqc_t_comm_destroy.
+  std::vector<mpqc_t_handle*> cached;
 };

@@ -398,12 +398,11 @@ int stage_in(Staged& s, const double* src, size_t n, bool on_device, const CommV
 // additionally keep on the device (staged factors ...), for the feasibility check.
 int alloc_operands(mpqc_t_handle* h, int npanel, double extra_bytes) {
   const int64_t o = h->o, v = h->v;
-  cudaFree(h->A);
-  cudaFree(h->AT);
-  h->A = h->AT = nullptr;
-  free_work(h);
   size_t free_b = 0, total_b = 0;
   MPQC_T_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  // a re-used handle (communicator cache) already holds a pool: count it as available, keep it if it still fits the plan
+  const double held = (h->A ? 1.0 : 0.0) * (double)h->npanel * v * v * h->Kp * 8.0 * (h->AT ? 2.0 : 1.0);
+  free_b += (size_t)held;
   // "flat" mode keeps a transposed copy AT of the big operand so both GEMM terms read 128 consecutive
   // flattened (p,q) rows (no row-patch padding).  Use it when 2|A| + the rest leaves >= 25% of free HBM.
   const double a_bytes = (double)npanel * v * v * h->Kp * 8.0;
@@ -423,10 +422,20 @@ int alloc_operands(mpqc_t_handle* h, int npanel, double extra_bytes) {
              extra_bytes * 1e-9, (double)free_b * 1e-9, h->device);
     return fail(MPQC_T_ERR_OOM, buf, __FILE__, __LINE__);
   }
-  h->npanel = npanel;
+  const bool keep = h->A != nullptr && h->npanel == npanel && ((h->AT != nullptr) == (h->flat != 0));
+  if (!keep) {
+    cudaFree(h->A);
+    cudaFree(h->AT);
+    h->A = h->AT = nullptr;
+    free_work(h);
+    h->npanel = npanel;
+    MPQC_T_CUDA(cudaMalloc(&h->A, (size_t)npanel * v * v * h->Kp * sizeof(double)));
+    if (h->flat) MPQC_T_CUDA(cudaMalloc(&h->AT, (size_t)npanel * v * v * h->Kp * sizeof(double)));
+  }
   h->panel_mode = npanel < o;
-  MPQC_T_CUDA(cudaMalloc(&h->A, (size_t)npanel * v * v * h->Kp * sizeof(double)));
-  if (h->flat) MPQC_T_CUDA(cudaMalloc(&h->AT, (size_t)npanel * v * v * h->Kp * sizeof(double)));
+  h->panels_built = 0;
+  cudaFree(h->slot_map_dev);
+  h->slot_map_dev = nullptr;
   MPQC_T_TRY(plan(h));
   MPQC_T_TRY(make_maps(h));
   h->slot_of.assign((size_t)o, -1);
@@ -696,6 +705,7 @@ int upload_df_impl(mpqc_t_handle* h, const mpqc_t_df_problem* p, bool on_device,
   const double w_one = 3.0 * (double)v * v * (double)roundup(v, 16) * 8.0;
   size_t free_b = 0, total_b = 0;
   MPQC_T_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  free_b += (size_t)((h->A ? 1.0 : 0.0) * (double)h->npanel * panel_bytes * (h->AT ? 2.0 : 1.0));   // a re-used pool
   int npanel = (int)o;
   if (block > 0) {
     npanel = (int)std::min<int64_t>(o, 3LL * block);
@@ -1537,7 +1547,14 @@ int energy_impl(const int64_t prob_o, const int64_t prob_v, const UploadFn& uplo
     const int wrank = comm ? cv.rank : g;
     mpqc_t_handle* h = nullptr;
     const double tw0 = now_s();
-    int rc = mpqc_t_create(&h, prob_o, prob_v, devs[g]);
+    if (comm && (int)comm->cached.size() > g && comm->cached[(size_t)g]) {
+      // device memory of the previous call on this member: re-used when the problem has the same shape
+      mpqc_t_handle* c = comm->cached[(size_t)g];
+      comm->cached[(size_t)g] = nullptr;
+      if (c->o == prob_o && c->v == prob_v && c->device == devs[g]) h = c;
+      else mpqc_t_destroy(c);
+    }
+    int rc = h ? MPQC_T_OK : mpqc_t_create(&h, prob_o, prob_v, devs[g]);
     if (rc == MPQC_T_OK) h->df_block = opt.df_block;
     cudaStream_t cst = nullptr;                       // stream of this worker's collectives
     if (exchange) {
@@ -1643,7 +1660,8 @@ int energy_impl(const int64_t prob_o, const int64_t prob_v, const UploadFn& uplo
     if (rc != MPQC_T_OK) msgs[g] = last_error_string();
     const double tw3 = now_s();
     if (!h && cst) cudaStreamDestroy(cst);
-    mpqc_t_destroy(h);
+    if (comm && rc == MPQC_T_OK && (int)comm->cached.size() > g) comm->cached[(size_t)g] = h;   // keep the memory for the next call
+    else mpqc_t_destroy(h);
     if (opt.verbose >= 2)
       printf("  [mpqc_t] rank %d gpu %d: create %.3f s, upload+relayout %.3f s, triples+sum %.3f s, destroy %.3f s\n", wrank,
              devs[g], tw1 - tw0, tw2 - tw1, tw3 - tw2, now_s() - tw3);
@@ -1776,6 +1794,7 @@ int mpqc_t_comm_create_rank(mpqc_t_comm** out, int32_t nranks, int32_t rank, con
   c->nranks = nranks;
   c->local = nranks == 1;
   c->members.resize(1);
+  c->cached.assign(1, nullptr);
   c->members[0].rank = rank;
   c->members[0].device = device;
   int rc = comm_member_init(c->members[0]);
@@ -1814,6 +1833,7 @@ int mpqc_t_comm_create_local(mpqc_t_comm** out, int32_t ngpu, const int32_t* dev
   c->nranks = ngpu;
   c->local = true;
   c->members.resize(ngpu);
+  c->cached.assign((size_t)ngpu, nullptr);
   // CUDA contexts are created here, one thread per device, so that the serial seconds of context creation in a
   // process that drives 8 GPUs are paid once and in parallel, outside the (T) call
   std::vector<int> rcs(ngpu, MPQC_T_OK);
@@ -1854,8 +1874,18 @@ int mpqc_t_comm_create_local(mpqc_t_comm** out, int32_t ngpu, const int32_t* dev
   return MPQC_T_OK;
 }
 
+int mpqc_t_comm_release_cache(mpqc_t_comm* c) {
+  if (!c) return MPQC_T_OK;
+  for (mpqc_t_handle*& h : c->cached) {
+    mpqc_t_destroy(h);
+    h = nullptr;
+  }
+  return MPQC_T_OK;
+}
+
 int mpqc_t_comm_destroy(mpqc_t_comm* c) {
   if (!c) return MPQC_T_OK;
+  mpqc_t_comm_release_cache(c);
   const NcclApi& nc = nccl_api();
   for (CommMember& m : c->members) {
     cudaSetDevice(m.device);

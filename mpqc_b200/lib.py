@@ -75,7 +75,7 @@ class MpqcTError(RuntimeError):
 #: every symbol include/mpqc_t.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "mpqc_t_energy", "mpqc_t_energy_df", "mpqc_t_create", "mpqc_t_upload", "mpqc_t_upload_df", "mpqc_t_run", "mpqc_t_debug_w", "mpqc_t_stream",
-    "mpqc_t_comm_unique_id", "mpqc_t_comm_create_rank", "mpqc_t_comm_create_local", "mpqc_t_comm_size", "mpqc_t_comm_destroy",
+    "mpqc_t_comm_unique_id", "mpqc_t_comm_create_rank", "mpqc_t_comm_create_local", "mpqc_t_comm_size", "mpqc_t_comm_release_cache", "mpqc_t_comm_destroy",
     "mpqc_t_energy_comm", "mpqc_t_energy_df_comm", "mpqc_t_host_alloc", "mpqc_t_host_free", "mpqc_t_run_vblocks", "mpqc_t_run_comm", "mpqc_t_set_df_block", "mpqc_t_plan_df", "mpqc_t_query", "mpqc_t_w_batch",
     "mpqc_t_destroy", "mpqc_t_triple_count", "mpqc_t_triple_of_unit", "mpqc_t_flops", "mpqc_t_unit_flops",
     "mpqc_t_device_count", "mpqc_t_plan", "mpqc_t_version", "mpqc_t_strerror", "mpqc_t_last_error", "mpqc_t_microbench",
@@ -132,6 +132,8 @@ def load() -> C.CDLL:
     lib.mpqc_t_comm_create_local.restype = C.c_int
     lib.mpqc_t_comm_size.argtypes = [vp]
     lib.mpqc_t_comm_size.restype = C.c_int
+    lib.mpqc_t_comm_release_cache.argtypes = [vp]
+    lib.mpqc_t_comm_release_cache.restype = C.c_int
     lib.mpqc_t_comm_destroy.argtypes = [vp]
     lib.mpqc_t_comm_destroy.restype = C.c_int
     lib.mpqc_t_energy_comm.argtypes = [vp, C.POINTER(Problem), C.POINTER(Options), c_double_p, C.POINTER(Stats)]
