@@ -629,47 +629,47 @@ int launch_plain_gemm(mpqc_t_handle* h, const PlainGemm& g, int64_t* launches) {
   return MPQC_T_OK;
 }
 
-// particle + hole part of the operand panels of occupied indices x0 .. x0+nx-1 into pool slots slot0 .. (consecutive)
+// Operand panels of occupied indices x0 .. x0+nx-1 into pool slots slot0 .. (consecutive).  The particle part is ONE
+// plain GEMM per call whose rows are the flattened (x, p) pairs of all nx panels (no row padding per panel: consecutive
+// slots are v rows of pitch v*Kp apart, so row m = (x - x0)*v + p lands at slot0*pstride + m*(v*Kp)), batched over q;
+// in panel-cache mode the hole part is copied from t2; in flat mode the transposed copy AT_x is then a row-wise
+// transposing copy of the finished panel (HBM-bound, ~10x cheaper than a second GEMM).  In resident mode the caller has
+// written the hole part of A before.
 int build_panels(mpqc_t_handle* h, int x0, int nx, int slot0, int64_t* launches) {
   const int64_t o = h->o, v = h->v, Kp = h->Kp;
   const int64_t pstride = v * v * Kp;
   PlainGemm g;
-  g.L = h->XaiT + (int64_t)x0 * v * h->Kx;   // batch entry b = (x - x0) * v + q
-  g.l_batches = nx;
-  g.M = v;
-  g.R = h->XabT;
+  g.L = h->XaiT + (int64_t)x0 * v * h->Kx;   // rows (x, p), x = x0 .. x0+nx-1
+  g.l_batches = 1;
+  g.M = (int64_t)nx * v;
+  g.R = h->XabT;                             // batch entry q: R_q[kap][K] = Xab[K][kap][q]
   g.r_batches = v;
   g.N = v;
   g.Kx = h->Kx;
-  g.nbatch = nx * (int)v;
-  g.l_div = (int)v;
-  g.l_mod = nx;
+  g.nbatch = (int)v;
+  g.l_div = 1;
+  g.l_mod = 1;
   g.r_div = 1;
   g.r_mod = (int)v;
-  g.o_div = (int)v;
-  // A[slot][p][q][kap]: row p has pitch v*Kp, batch entry (x, q) starts at slot*pstride + q*Kp
-  g.out = h->A + (int64_t)slot0 * pstride;
-  g.out_s1 = pstride;
-  g.out_s2 = Kp;
+  g.o_div = 1;
+  g.out = h->A + (int64_t)slot0 * pstride;   // C_q[(x,p)][kap] -> A[slot][p][q][kap]
+  g.out_s1 = Kp;
+  g.out_s2 = 0;
   g.ldw = v * Kp;
   MPQC_T_TRY(launch_plain_gemm(h, g, launches));
-  if (h->flat) {
-    // AT[slot][p][q][kap] = A[slot][q][p][kap]: batch entry (x, p), row q has pitch Kp
-    g.out = h->AT + (int64_t)slot0 * pstride;
-    g.out_s2 = v * Kp;
-    g.ldw = Kp;
-    MPQC_T_TRY(launch_plain_gemm(h, g, launches));
-  }
-  if (h->panel_mode) {
-    const int64_t total = v * v * o;
-    const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, 148 * 32);
-    for (int x = x0; x < x0 + nx; ++x) {
-      const int s = slot0 + (x - x0);
-      copy_hole_panel_kernel<<<blocks, 256, 0, h->stream>>>(h->T2raw, h->A + (int64_t)s * pstride, v, o, x, Kp, 0);
-      if (h->flat)
-        copy_hole_panel_kernel<<<blocks, 256, 0, h->stream>>>(h->T2raw, h->AT + (int64_t)s * pstride, v, o, x, Kp, 1);
+  const unsigned cblocks = (unsigned)std::min<int64_t>((v * v * o + 255) / 256, 148 * 32);
+  const unsigned tblocks = (unsigned)std::min<int64_t>((v * v + 7) / 8, 148 * 16);
+  for (int x = x0; x < x0 + nx; ++x) {
+    const int s = slot0 + (x - x0);
+    if (h->panel_mode) {
+      copy_hole_panel_kernel<<<cblocks, 256, 0, h->stream>>>(h->T2raw, h->A + (int64_t)s * pstride, v, o, x, Kp, 0);
       MPQC_T_CUDA(cudaGetLastError());
-      if (launches) *launches += h->flat ? 2 : 1;
+      if (launches) ++*launches;
+    }
+    if (h->flat) {
+      transpose_panel_kernel<<<tblocks, 256, 0, h->stream>>>(h->A + (int64_t)s * pstride, h->AT + (int64_t)s * pstride, v, Kp);
+      MPQC_T_CUDA(cudaGetLastError());
+      if (launches) ++*launches;
     }
   }
   h->panels_built += nx;
@@ -763,10 +763,8 @@ int upload_df_impl(mpqc_t_handle* h, const mpqc_t_df_problem* p, bool on_device,
       MPQC_T_CUDA(cudaMalloc(&h->T2raw, (size_t)v * v * o * o * sizeof(double)));
       MPQC_T_CUDA(cudaMemcpyAsync(h->T2raw, t2.ptr, (size_t)v * v * o * o * sizeof(double), cudaMemcpyDeviceToDevice, st));
       MPQC_T_CUDA(cudaMalloc(&h->slot_map_dev, (size_t)o * sizeof(int)));
-    } else {
+    } else {   // resident: hole part of every panel now; AT is copied from the finished panels in build_panels
       MPQC_T_TRY(launch_copy_hole(st, t2.ptr, h->A, v * v, o, o, v, v * Kp, Kp, v * v * Kp, v, -1.0, &launches));
-      if (h->flat)
-        MPQC_T_TRY(launch_copy_hole(st, t2.ptr, h->AT, v * v, o, o, v, Kp, v * Kp, v * v * Kp, v, -1.0, &launches));
     }
     MPQC_T_CUDA(cudaStreamSynchronize(st));   // staged raw inputs are released here
   }
@@ -912,10 +910,9 @@ int run_units_panels(mpqc_t_handle* h, const std::vector<int>& tri, int64_t n, i
     stats->kernel_launches += launches;
     stats->flops += (double)n * mpqc_t_unit_flops(h->o, h->v);
     const double mpad = (double)h->nmt * kBM, npad = (double)h->nnt * h->tn - 8.0 * h->skip_last;
-    // executed: the triples themselves + the panels built for them (2 naux v^3 each, twice in flat mode)
+    // executed: the triples themselves + the panels built for them (2 naux v^3 each)
     stats->flops_executed += (double)n * 3.0 * 2.0 * 2.0 * mpad * npad * (double)h->Kp +
-                             (double)(h->panels_built - built0) * 2.0 * (double)h->Kx * (double)h->v * h->v * h->v *
-                                 (h->flat ? 2.0 : 1.0);
+                             (double)(h->panels_built - built0) * 2.0 * (double)h->Kx * (double)h->v * h->v * h->v;
     stats->bytes_d2h += n * 8;
     stats->bytes_h2d += n * 12;
   }
@@ -1244,8 +1241,8 @@ int mpqc_t_plan_df(int64_t o, int64_t v, int64_t naux, int32_t block, int32_t fl
   // panels built over the whole job ~ o^3 / (6 block^2) (one block of panels per occupied-block triple), 2 Kx v^3 FLOPs
   // each, against 2 o^3 v^3 (v+o) for the triples
   const double bo = (double)out->block;
-  out->build_flop_fraction = out->panel_mode ? (Kx / (6.0 * bo * bo * (double)(v + o))) * (flat ? 2.0 : 1.0)
-                                             : (double)o * 2.0 * Kx * v * v * v * (flat ? 2.0 : 1.0) / mpqc_t_flops(o, v);
+  out->build_flop_fraction = out->panel_mode ? Kx / (6.0 * bo * bo * (double)(v + o))
+                                             : (double)o * 2.0 * Kx * v * v * v / mpqc_t_flops(o, v);
   return MPQC_T_OK;
 }
 

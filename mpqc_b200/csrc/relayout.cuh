@@ -73,6 +73,21 @@ copy_hole_panel_kernel(const double* __restrict__ t2, double* __restrict__ panel
   }
 }
 
+// AT_x[p][q][:] = A_x[q][p][:]: the transposed copy of one complete operand panel (particle AND hole part), whole rows
+// of Kp doubles at a time (16-byte vectors; Kp is a multiple of 8).  One warp per row, HBM-bound.
+__global__ void __launch_bounds__(256)
+transpose_panel_kernel(const double* __restrict__ a, double* __restrict__ at, int64_t v, int64_t Kp) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t nvec = Kp / 2;
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < v * v; row += warps) {
+    const int64_t p = row / v, q = row % v;
+    const double2* src = reinterpret_cast<const double2*>(a + (q * v + p) * Kp);
+    double2* dst = reinterpret_cast<double2*>(at + row * Kp);
+    for (int64_t c = lane; c < nvec; c += 32) dst[c] = __ldg(src + c);
+  }
+}
+
 inline int launch_transpose(cudaStream_t st, const double* in, double* out, int64_t nk, int64_t nmid,
                             int64_t nj, int64_t jdiv, int64_t s1, int64_t s2, int64_t s3,
                             int64_t* launches) {
