@@ -200,6 +200,41 @@ def test_uracil_dimer_whole_job_vs_sampled_coarse_iterations(lib):
         assert abs(vb[g - 1] - e_block) < TOL, (g, vb[g - 1], e_block)
 
 
+def test_infeasible_problem_is_refused_with_numbers(lib):
+    # the accepted (o, v) range is far wider than one device: the library must say so (MPQC_T_ERR_OOM -> MemAllocFailed
+    # with the byte counts) instead of dying in some later allocation or launching with a truncated workspace
+    h = C.c_void_p()
+    assert lib.mpqc_t_create(C.byref(h), 4096, 2040, 0) == L.ERR_OOM and not h.value
+    # o=60, v=900: B and GV fit (25 + 23 GB), the operand panels (373 GB) do not -> refused at upload, before any input
+    # byte is read (the pointers below are dummies)
+    L.check(lib.mpqc_t_create(C.byref(h), 60, 900, 0), "create")
+    dummy = torch.zeros(8, dtype=torch.float64, device="cuda")
+    prob = L.Problem(o=60, v=900, **{k: dummy.data_ptr() for k in ("eps_occ", "eps_vir", "t1", "t2", "g_abij", "g_aijk", "g_abci")})
+    assert lib.mpqc_t_upload(h, C.byref(prob), 1, None) == L.ERR_OOM
+    msg = lib.mpqc_t_last_error().decode()
+    assert "needs" in msg and "GB" in msg and "o=60 v=900" in msg, msg
+    e = C.c_double()
+    assert lib.mpqc_t_run(h, 0, 1, 1, 0, C.byref(e), None, None) == L.ERR_BAD_ARG      # nothing was uploaded
+    lib.mpqc_t_destroy(h)
+    # the density-fitted hand-off of the same shape falls back to a panel cache on its own instead of refusing
+    info = L.DfPlanInfo()
+    assert lib.mpqc_t_plan_df(60, 900, 3000, 3, 0, C.byref(info)) == L.OK and info.bytes_total < 170e9
+
+
+def test_plugin_mirror_through_a_library_communicator(lib):
+    # CCSD_T(..., comm=): the call becomes mpqc_t_energy_comm and returns the TOTAL E(T)
+    p = make_problem(5, 20, seed=8)
+    comm = C.c_void_p()
+    L.check(lib.mpqc_t_comm_create_rank(C.byref(comm), 1, 0, None, 0), "comm_create_rank")
+    try:
+        wfn = CCSD_T({"type": "CCSD(T)"}, ccsd=DenseCCSD.from_problem(p), out=io.StringIO(), comm=comm)
+        assert abs(wfn.compute_ccsd_t() - oc.ijk_driven(*_args(p))) < TOL
+        with pytest.raises(Exception):
+            CCSD_T({"rank": 0, "world_size": 2}, ccsd=DenseCCSD.from_problem(p), comm=comm)
+    finally:
+        lib.mpqc_t_comm_destroy(comm)
+
+
 def test_rank_mode_communicator_of_one(lib):
     # mpqc_t_energy_comm through a one-rank communicator must be the plain call (no NCCL exchange involved)
     p = make_problem(6, 22, seed=19)
