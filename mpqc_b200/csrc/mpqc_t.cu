@@ -136,6 +136,10 @@ struct mpqc_t_handle {
   double *XaiT = nullptr, *XabT = nullptr, *T2raw = nullptr;   // [o][v][Kx], [v][v][Kx], t2[v][v][o][o] (panel mode)
   int64_t Kx = 0;                  // padded auxiliary dimension roundup8(naux) (>= 16)
   int64_t panels_built = 0;
+  // staging arena of the uploads (raw input copies, <ia|bc> slabs): one allocation that lives with the handle, bump
+  // allocated per upload -- cudaMalloc/cudaFree of GBs per call were measured at tens of ms per GB on some hosts
+  double* arena = nullptr;
+  size_t arena_cap = 0, arena_used = 0;
 };
 
 namespace {
@@ -379,20 +383,46 @@ int replicate_from_host(const CommView& cv, double* dst, const double* src, size
   return rc;
 }
 
-// host tensor -> device copy (sharded + all-gathered when a communicator is present), or an alias of a device pointer
+// staging arena: reserve once per upload (grows only), then bump-allocate 256-byte aligned pieces
+int arena_reserve(mpqc_t_handle* h, size_t doubles) {
+  h->arena_used = 0;
+  if (doubles <= h->arena_cap) return MPQC_T_OK;
+  cudaFree(h->arena);
+  h->arena = nullptr;
+  h->arena_cap = 0;
+  MPQC_T_CUDA(cudaMalloc(&h->arena, std::max<size_t>(doubles, 32) * sizeof(double)));
+  h->arena_cap = doubles;
+  return MPQC_T_OK;
+}
+
+inline size_t arena_round(size_t doubles) { return (doubles + 31) / 32 * 32; }
+
+double* arena_take(mpqc_t_handle* h, size_t doubles) {
+  const size_t need = arena_round(doubles);
+  if (h->arena_used + need > h->arena_cap) return nullptr;
+  double* p = h->arena + h->arena_used;
+  h->arena_used += need;
+  return p;
+}
+
+// host tensor -> device copy in the handle's staging arena (sharded + all-gathered when a communicator is present), or
+// an alias of a device pointer
 struct Staged {
   const double* ptr = nullptr;
-  DevBuf owned;
 };
 
-int stage_in(Staged& s, const double* src, size_t n, bool on_device, const CommView& cv, cudaStream_t st, int64_t* h2d) {
+inline size_t staged_size(size_t n, bool on_device, int nranks) { return on_device ? 0 : arena_round(padded_count(n, nranks)); }
+
+int stage_in(mpqc_t_handle* h, Staged& s, const double* src, size_t n, bool on_device, const CommView& cv, cudaStream_t st,
+             int64_t* h2d) {
   if (on_device) {
     s.ptr = src;
     return MPQC_T_OK;
   }
-  MPQC_T_TRY(s.owned.alloc(padded_count(n, cv.nranks)));
-  MPQC_T_TRY(replicate_from_host(cv, s.owned.p, src, n, st, h2d));
-  s.ptr = s.owned.p;
+  double* dst = arena_take(h, padded_count(n, cv.nranks));
+  MPQC_T_CHECK(dst != nullptr, MPQC_T_ERR_INTERNAL, "staging arena too small");
+  MPQC_T_TRY(replicate_from_host(cv, dst, src, n, st, h2d));
+  s.ptr = dst;
   return MPQC_T_OK;
 }
 
@@ -456,8 +486,19 @@ int upload_impl(mpqc_t_handle* h, const mpqc_t_problem* p, bool on_device, const
   const double t0 = now_s();
   double t_copy = 0.0;
   h->uploaded = false;
-  // dense inputs: all o panels resident; transient staging = t2 + g_abij + g_aijk copies and two <ia|bc> slabs
-  MPQC_T_TRY(alloc_operands(h, (int)o, on_device ? 0.0 : (2.0 * v * v * o * o + (double)v * o * o * o) * 8.0 + 2.2e9));
+  // <ia|bc> streams through slabs of whole kap rows (host inputs)
+  const size_t row = (size_t)v * v * o;  // doubles per kap
+  const size_t slab_bytes = cv.nranks > 1 ? (size_t(2) << 30) : (size_t(1) << 30);
+  const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(v, (int64_t)(slab_bytes / (row * 8 + 1)) + 1));
+  // staging arena: raw copies of t1, t2, g_abij, g_aijk and two slabs (nothing when the inputs are on the device)
+  const size_t arena_need = on_device ? 0
+                                      : staged_size((size_t)v * o, false, 1) + 2 * staged_size((size_t)v * v * o * o, false, cv.nranks) +
+                                            staged_size((size_t)v * o * o * o, false, cv.nranks) +
+                                            2 * arena_round(padded_count((size_t)slab * row, cv.nranks));
+  const double arena_new = arena_need > h->arena_cap ? (double)arena_need * 8.0 : 0.0;
+  // dense inputs: all o panels resident
+  MPQC_T_TRY(alloc_operands(h, (int)o, arena_new));
+  MPQC_T_TRY(arena_reserve(h, arena_need));
   // Ordering contract (include/mpqc_t.h): device-resident inputs may have been produced on any stream of the caller;
   // the handle's stream is non-blocking, so wait for the whole device before reading them.
   if (on_device) MPQC_T_CUDA(cudaDeviceSynchronize());
@@ -474,10 +515,10 @@ int upload_impl(mpqc_t_handle* h, const mpqc_t_problem* p, bool on_device, const
     if (!on_device) h2d += (o + v) * 8;
     Staged t1, t2, gabij, gaijk;
     CommView solo;   // the tiny t1 is copied whole by every rank
-    MPQC_T_TRY(stage_in(t1, p->t1, (size_t)v * o, on_device, solo, st, &h2d));
-    MPQC_T_TRY(stage_in(t2, p->t2, (size_t)v * v * o * o, on_device, cv, st, &h2d));
-    MPQC_T_TRY(stage_in(gabij, p->g_abij, (size_t)v * v * o * o, on_device, cv, st, &h2d));
-    MPQC_T_TRY(stage_in(gaijk, p->g_aijk, (size_t)v * o * o * o, on_device, cv, st, &h2d));
+    MPQC_T_TRY(stage_in(h, t1, p->t1, (size_t)v * o, on_device, solo, st, &h2d));
+    MPQC_T_TRY(stage_in(h, t2, p->t2, (size_t)v * v * o * o, on_device, cv, st, &h2d));
+    MPQC_T_TRY(stage_in(h, gabij, p->g_abij, (size_t)v * v * o * o, on_device, cv, st, &h2d));
+    MPQC_T_TRY(stage_in(h, gaijk, p->g_aijk, (size_t)v * o * o * o, on_device, cv, st, &h2d));
     if (!on_device) {
       MPQC_T_CUDA(cudaStreamSynchronize(st));
       t_copy += now_s() - tc;
@@ -494,7 +535,7 @@ int upload_impl(mpqc_t_handle* h, const mpqc_t_problem* p, bool on_device, const
     MPQC_T_TRY(launch_copy_hole(st, t2.ptr, h->A, v * v, o, o, v, v * Kp, Kp, v * v * Kp, v, -1.0, &launches));
     if (h->flat)
       MPQC_T_TRY(launch_copy_hole(st, t2.ptr, h->AT, v * v, o, o, v, Kp, v * Kp, v * v * Kp, v, -1.0, &launches));
-    MPQC_T_CUDA(cudaStreamSynchronize(st));  // staged buffers are freed on scope exit
+    MPQC_T_CUDA(cudaStreamSynchronize(st));
   }
 
   // A particle part: g_abci[kap][p][(q,x)] -> A[x][p][q][kap], streamed in kap slabs
@@ -507,11 +548,11 @@ int upload_impl(mpqc_t_handle* h, const mpqc_t_problem* p, bool on_device, const
     // slabs of whole kap rows; each slab crosses PCIe once in total (1/nranks of it per rank) and is completed by an
     // all-gather, then transposed into place.  Two slabs so that the copy of the next one is queued while the
     // transposes of the current one run.
-    const size_t row = (size_t)v * v * o;  // doubles per kap
-    const size_t slab_bytes = cv.nranks > 1 ? (size_t(2) << 30) : (size_t(1) << 30);
-    const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(v, (int64_t)(slab_bytes / (row * 8 + 1)) + 1));
-    DevBuf buf[2];
-    for (int s = 0; s < 2; ++s) MPQC_T_TRY(buf[s].alloc(padded_count((size_t)slab * row, cv.nranks)));
+    struct { double* p; } buf[2];
+    for (int s = 0; s < 2; ++s) {
+      buf[s].p = arena_take(h, padded_count((size_t)slab * row, cv.nranks));
+      MPQC_T_CHECK(buf[s].p != nullptr, MPQC_T_ERR_INTERNAL, "staging arena too small");
+    }
     EventList events;               // copy (+ all-gather) time of every slab, device-timed on the handle's stream
     std::vector<cudaEvent_t> ev;
     int which = 0;
@@ -735,11 +776,15 @@ int upload_df_impl(mpqc_t_handle* h, const mpqc_t_df_problem* p, bool on_device,
   {
     Staged t1, t2, xab, xij, xai;
     CommView solo;
-    MPQC_T_TRY(stage_in(t1, p->t1, (size_t)v * o, on_device, solo, st, &h2d));
-    MPQC_T_TRY(stage_in(t2, p->t2, (size_t)v * v * o * o, on_device, cv, st, &h2d));
-    MPQC_T_TRY(stage_in(xab, p->x_ab, (size_t)naux * v * v, on_device, cv, st, &h2d));
-    MPQC_T_TRY(stage_in(xij, p->x_ij, (size_t)naux * o * o, on_device, solo, st, &h2d));
-    MPQC_T_TRY(stage_in(xai, p->x_ai, (size_t)naux * v * o, on_device, cv, st, &h2d));
+    MPQC_T_TRY(arena_reserve(h, staged_size((size_t)v * o, on_device, 1) + staged_size((size_t)v * v * o * o, on_device, cv.nranks) +
+                                    staged_size((size_t)naux * v * v, on_device, cv.nranks) +
+                                    staged_size((size_t)naux * o * o, on_device, 1) +
+                                    staged_size((size_t)naux * v * o, on_device, cv.nranks)));
+    MPQC_T_TRY(stage_in(h, t1, p->t1, (size_t)v * o, on_device, solo, st, &h2d));
+    MPQC_T_TRY(stage_in(h, t2, p->t2, (size_t)v * v * o * o, on_device, cv, st, &h2d));
+    MPQC_T_TRY(stage_in(h, xab, p->x_ab, (size_t)naux * v * v, on_device, cv, st, &h2d));
+    MPQC_T_TRY(stage_in(h, xij, p->x_ij, (size_t)naux * o * o, on_device, solo, st, &h2d));
+    MPQC_T_TRY(stage_in(h, xai, p->x_ai, (size_t)naux * v * o, on_device, cv, st, &h2d));
     if (!on_device) {
       MPQC_T_CUDA(cudaStreamSynchronize(st));
       t_copy += now_s() - tc;
@@ -769,7 +814,7 @@ int upload_df_impl(mpqc_t_handle* h, const mpqc_t_df_problem* p, bool on_device,
     } else {   // resident: hole part of every panel now; AT is copied from the finished panels in build_panels
       MPQC_T_TRY(launch_copy_hole(st, t2.ptr, h->A, v * v, o, o, v, v * Kp, Kp, v * v * Kp, v, -1.0, &launches));
     }
-    MPQC_T_CUDA(cudaStreamSynchronize(st));   // staged raw inputs are released here
+    MPQC_T_CUDA(cudaStreamSynchronize(st));
   }
 
   PlainGemm g;
@@ -1191,6 +1236,7 @@ int mpqc_t_destroy(mpqc_t_handle* h) {
   cudaFree(h->tile_sets);
   cudaFree(h->triples_dev);
   cudaFree(h->unit_e_dev);
+  cudaFree(h->arena);
   cudaFree(h->slot_map_dev);
   cudaFree(h->XaiT);
   cudaFree(h->XabT);
