@@ -216,6 +216,13 @@ int mpqc_t_destroy(mpqc_t_handle* h);
 int64_t mpqc_t_triple_count(int64_t o);
 /* unit index -> (i,j,k) of the enumeration above; returns MPQC_T_ERR_BAD_ARG when out of range */
 int mpqc_t_triple_of_unit(int64_t o, int64_t unit, int32_t* i, int32_t* j, int32_t* k);
+/* Host-only: which positions of the job (first, first+stride, ...; count of them, <0 = all) worker `rank` of `nranks` runs
+ * statically -- exactly what mpqc_t_energy[_comm] does inside.  panel_block = 0: unit-cyclic (rank, rank+nranks, ...);
+ * when all workers share a process (all_local) only the first 7/8 are static and *tail_begin is where the work-stealing
+ * tail starts.  panel_block > 0 (operand panel cache): occupied-block groups dealt largest-first to the least loaded
+ * worker.  Returns the number of positions (written to positions[0..capacity)), or -1 on bad arguments. */
+int64_t mpqc_t_shard_plan(int64_t o, int64_t first, int64_t stride, int64_t count, int32_t nranks, int32_t rank,
+                          int32_t all_local, int32_t panel_block, int64_t* positions, int64_t capacity, int64_t* tail_begin);
 double mpqc_t_flops(int64_t o, int64_t v);           /* 2 o^3 v^3 (v+o), the published work model */
 double mpqc_t_unit_flops(int64_t o, int64_t v);      /* 12 v^3 (v+o) */
 int mpqc_t_device_count(void);

@@ -49,6 +49,52 @@ int validate_problem(const mpqc_t_problem* p) {
 
 typedef std::function<int(mpqc_t_handle*, const CommView&, mpqc_t_stats*)> UploadFn;
 
+// Static share of a job among W workers (host only; also exported as mpqc_t_shard_plan so the split can be tested
+// without a GPU).  Job positions are 0-based indices into the job  first, first+stride, ...  (count of them).
+//   panel_block == 0: unit-cyclic -- worker w takes positions w, w+W, ... below `static_n`; when all workers share a
+//     process, static_n = the first 7/8 (a multiple of W) and the rest is handed out at run time by an atomic counter
+//     (work stealing); otherwise static_n = count.
+//   panel_block  > 0 (operand panel cache): shard by occupied-block triple, not by unit -- a worker that holds a
+//     group's panels runs the whole group.  Groups are dealt largest-first to the least loaded worker: every rank
+//     computes the same assignment.
+int64_t static_share_end(int64_t count, int W, bool all_local, int panel_block) {
+  if (panel_block > 0) return count;
+  return (W > 1 && all_local) ? (count / 8) * 7 / W * W : count;
+}
+
+void static_share(const UnitIndex& ux, int64_t first, int64_t stride, int64_t count, int W, int wrank, bool all_local,
+                  int panel_block, std::vector<int64_t>& mine) {
+  mine.clear();
+  if (panel_block <= 0) {
+    const int64_t static_n = static_share_end(count, W, all_local, 0);
+    for (int64_t q = wrank; q < static_n; q += W) mine.push_back(q);
+    return;
+  }
+  std::vector<std::pair<int64_t, int64_t>> keyed((size_t)count);   // (group key, job position)
+  for (int64_t q = 0; q < count; ++q) {
+    int i, j, k;
+    ux.triple(first + q * stride, i, j, k);
+    keyed[(size_t)q] = std::make_pair(block_key(i, j, k, panel_block), q);
+  }
+  std::sort(keyed.begin(), keyed.end());
+  std::vector<std::pair<int64_t, int64_t>> groups;                  // (size, first index into keyed)
+  for (int64_t a = 0; a < count;) {
+    int64_t b = a;
+    while (b < count && keyed[(size_t)b].first == keyed[(size_t)a].first) ++b;
+    groups.push_back(std::make_pair(b - a, a));
+    a = b;
+  }
+  std::stable_sort(groups.begin(), groups.end(),
+                   [](const std::pair<int64_t, int64_t>& x, const std::pair<int64_t, int64_t>& y) { return x.first > y.first; });
+  std::vector<int64_t> load((size_t)W, 0);
+  for (const auto& gsz : groups) {
+    const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+    load[(size_t)w] += gsz.first;
+    if (w == wrank)
+      for (int64_t a = gsz.second; a < gsz.second + gsz.first; ++a) mine.push_back(keyed[(size_t)a].second);
+  }
+}
+
 // Shared driver of the one-shot entry points.  The job is the unit list  first, first+stride, ... (count of them);
 // it is sharded over the W workers of the communicator (worker w takes job positions w, w+W, ...; when every worker
 // lives in this process the last 1/8 is handed out by an atomic counter instead -- work stealing), each worker
@@ -115,8 +161,7 @@ int energy_impl(const int64_t prob_o, const int64_t prob_v, const UploadFn& uplo
   std::vector<double> unit_e((size_t)count, 0.0);   // each slot is written by exactly one worker thread
   const int W = comm ? nranks : nlocal;              // workers over which the job is split
   const bool all_local = !comm || comm->local;       // work stealing needs shared memory
-  const int64_t static_n = (W > 1 && all_local) ? (count / 8) * 7 / W * W : count;
-  std::atomic<int64_t> tail_next(static_n);
+  std::atomic<int64_t> tail_next(static_share_end(count, W, all_local, 0));   // first position of the work-stealing tail
   const bool profile = getenv("MPQC_T_PROFILE") != nullptr;
 
   std::vector<mpqc_t_stats> gstats(nlocal);
@@ -156,46 +201,12 @@ int energy_impl(const int64_t prob_o, const int64_t prob_v, const UploadFn& uplo
     if (rc == MPQC_T_OK) rc = upload(h, cv, &gs);
     const double tw2 = now_s();
     std::vector<int64_t> done_idx;     // job positions this worker produced
-    if (rc == MPQC_T_OK && h->panel_mode) {
-      // Panel-cache mode: shard by occupied-block triple, not by unit -- a worker that holds a group's panels runs
-      // the whole group.  Groups are dealt largest-first to the least loaded worker (same answer on every rank).
-      const int bo = panel_block_edge(h);
-      std::vector<std::pair<int64_t, int64_t>> keyed((size_t)count);   // (group key, job position)
-      for (int64_t q = 0; q < count; ++q) {
-        int i, j, k;
-        ux.triple(opt.unit_first + q * stride, i, j, k);
-        keyed[(size_t)q] = std::make_pair(block_key(i, j, k, bo), q);
-      }
-      std::sort(keyed.begin(), keyed.end());
-      std::vector<std::pair<int64_t, int64_t>> groups;                  // (size, first index into keyed)
-      for (int64_t a = 0; a < count;) {
-        int64_t b = a;
-        while (b < count && keyed[(size_t)b].first == keyed[(size_t)a].first) ++b;
-        groups.push_back(std::make_pair(b - a, a));
-        a = b;
-      }
-      std::stable_sort(groups.begin(), groups.end(),
-                       [](const std::pair<int64_t, int64_t>& x, const std::pair<int64_t, int64_t>& y) { return x.first > y.first; });
-      std::vector<int64_t> load((size_t)W, 0), mine, idx;
-      for (const auto& gsz : groups) {
-        const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-        load[(size_t)w] += gsz.first;
-        if (w == wrank)
-          for (int64_t a = gsz.second; a < gsz.second + gsz.first; ++a) mine.push_back(keyed[(size_t)a].second);
-      }
-      idx.resize(mine.size());
-      std::vector<double> e(mine.size());
-      for (size_t q = 0; q < mine.size(); ++q) idx[q] = opt.unit_first + mine[q] * stride;
-      rc = run_units(h, ux, idx.data(), (int64_t)idx.size(), opt.batch, e.data(), &gs, profile);
-      if (rc == MPQC_T_OK)
-        for (size_t q = 0; q < mine.size(); ++q) {
-          unit_e[(size_t)mine[q]] = e[q];
-          done_idx.push_back(mine[q]);
-        }
-    } else if (rc == MPQC_T_OK) {
-      // static share
+    if (rc == MPQC_T_OK) {
+      // static share: unit-cyclic, or by occupied-block group in panel-cache mode (static_share above)
+      const int pblock = h->panel_mode ? panel_block_edge(h) : 0;
+      const int64_t my_static_n = static_share_end(count, W, all_local, pblock);   // == count in panel mode: no tail
       std::vector<int64_t> mine, idx;
-      for (int64_t q = wrank; q < static_n; q += W) mine.push_back(q);
+      static_share(ux, opt.unit_first, stride, count, W, wrank, all_local, pblock, mine);
       idx.resize(mine.size());
       std::vector<double> e(mine.size());
       for (size_t q = 0; q < mine.size(); ++q) idx[q] = opt.unit_first + mine[q] * stride;
@@ -207,7 +218,7 @@ int energy_impl(const int64_t prob_o, const int64_t prob_v, const UploadFn& uplo
         }
       // work-stealing tail (only when all workers share this process)
       const int64_t chunk = opt.steal_chunk > 0 ? opt.steal_chunk : std::max<int64_t>(1, auto_batch(h)) * 4;
-      while (rc == MPQC_T_OK && static_n < count) {
+      while (rc == MPQC_T_OK && my_static_n < count) {
         const int64_t s0 = tail_next.fetch_add(chunk);
         if (s0 >= count) break;
         const int64_t n = std::min(chunk, count - s0);

@@ -54,6 +54,25 @@ int mpqc_t_triple_of_unit(int64_t o, int64_t unit, int32_t* i, int32_t* j, int32
   return MPQC_T_OK;
 }
 
+int64_t mpqc_t_shard_plan(int64_t o, int64_t first, int64_t stride, int64_t count, int32_t nranks, int32_t rank,
+                          int32_t all_local, int32_t panel_block, int64_t* positions, int64_t capacity, int64_t* tail_begin) {
+  if (o < 1 || o > 4096 || nranks < 1 || rank < 0 || rank >= nranks || first < 0 || panel_block < 0) {
+    fail(MPQC_T_ERR_BAD_ARG, "bad shard plan arguments", __FILE__, __LINE__);
+    return -1;
+  }
+  if (stride <= 0) stride = 1;
+  const UnitIndex ux(o);
+  const int64_t nt = ux.count();
+  const int64_t avail = first < nt ? (nt - first + stride - 1) / stride : 0;
+  if (count < 0 || count > avail) count = avail;
+  std::vector<int64_t> mine;
+  static_share(ux, first, stride, count, nranks, rank, all_local != 0, panel_block, mine);
+  if (tail_begin) *tail_begin = static_share_end(count, nranks, all_local != 0, panel_block);
+  if (positions)
+    for (size_t q = 0; q < mine.size() && (int64_t)q < capacity; ++q) positions[q] = mine[q];
+  return (int64_t)mine.size();
+}
+
 double mpqc_t_flops(int64_t o, int64_t v) { return 2.0 * (double)o * o * o * (double)v * v * v * (double)(v + o); }
 double mpqc_t_unit_flops(int64_t o, int64_t v) { return 12.0 * (double)v * v * v * (double)(v + o); }
 

@@ -76,7 +76,7 @@ class MpqcTError(RuntimeError):
 SYMBOLS = [
     "mpqc_t_energy", "mpqc_t_energy_df", "mpqc_t_create", "mpqc_t_upload", "mpqc_t_upload_df", "mpqc_t_run", "mpqc_t_debug_w", "mpqc_t_stream",
     "mpqc_t_comm_unique_id", "mpqc_t_comm_create_rank", "mpqc_t_comm_create_local", "mpqc_t_comm_size", "mpqc_t_comm_release_cache", "mpqc_t_comm_destroy",
-    "mpqc_t_energy_comm", "mpqc_t_energy_df_comm", "mpqc_t_host_alloc", "mpqc_t_host_free", "mpqc_t_run_vblocks", "mpqc_t_run_comm", "mpqc_t_set_df_block", "mpqc_t_plan_df", "mpqc_t_query", "mpqc_t_w_batch",
+    "mpqc_t_energy_comm", "mpqc_t_energy_df_comm", "mpqc_t_host_alloc", "mpqc_t_host_free", "mpqc_t_run_vblocks", "mpqc_t_run_comm", "mpqc_t_set_df_block", "mpqc_t_plan_df", "mpqc_t_query", "mpqc_t_w_batch", "mpqc_t_shard_plan",
     "mpqc_t_destroy", "mpqc_t_triple_count", "mpqc_t_triple_of_unit", "mpqc_t_flops", "mpqc_t_unit_flops",
     "mpqc_t_device_count", "mpqc_t_plan", "mpqc_t_version", "mpqc_t_strerror", "mpqc_t_last_error", "mpqc_t_microbench",
 ]
@@ -116,6 +116,9 @@ def load() -> C.CDLL:
     lib.mpqc_t_run_comm.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int32, c_double_p, c_double_p,
                                     C.POINTER(Stats)]
     lib.mpqc_t_run_comm.restype = C.c_int
+    lib.mpqc_t_shard_plan.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                      C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64)]
+    lib.mpqc_t_shard_plan.restype = C.c_int64
     lib.mpqc_t_w_batch.argtypes = [vp, C.POINTER(C.c_int32), C.c_int64, vp, C.c_int32]
     lib.mpqc_t_w_batch.restype = C.c_int
     lib.mpqc_t_query.argtypes = [vp, C.c_int32, C.POINTER(C.c_int64)]

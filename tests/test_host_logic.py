@@ -124,6 +124,94 @@ def test_two_rank_sharding_gloo():
         assert abs(r[2] - ref) < 1e-12
 
 
+def _shard(lib, o, nranks, rank, all_local, panel_block, first=0, stride=1, count=-1):
+    import ctypes as C
+    n = lib.mpqc_t_triple_count(o)
+    buf = (C.c_int64 * n)()
+    tail = C.c_int64()
+    m = lib.mpqc_t_shard_plan(o, first, stride, count, nranks, rank, all_local, panel_block, buf, n, C.byref(tail))
+    return list(buf[:m]), tail.value
+
+
+def _plan_rank_main(rank, world, port, o, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mpqc_b200 import lib as L
+    lib = L.load()
+    p = make_problem(o, 5)
+    args = (p["t1"], p["t2"], p["g_abij"], p["g_aijk"], p["g_abci"], p["eps_occ"], p["eps_vir"])
+    units = oc.ijk_triple_list(o)
+    out = []
+    for panel_block in (0, 2):          # unit-cyclic, and occupied-block groups (panel-cache mode)
+        mine, _ = _shard(lib, o, world, rank, 0, panel_block)           # rank mode: the library's own split
+        partial = oc.ijk_driven(*args, triples=[units[u] for u in mine])
+        t = torch.tensor([partial], dtype=torch.float64)
+        dist.all_reduce(t)                                              # what ncclAllReduce does on the GPU box
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        out.append((panel_block, float(t[0]), gathered))
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_library_shard_plan_two_ranks_gloo():
+    # the split mpqc_t_energy_comm performs inside (host-only export mpqc_t_shard_plan), driven by two gloo ranks: the
+    # shards partition the job in both modes and the reduced energy is the oracle's
+    o = 6
+    p = make_problem(o, 5)
+    ref = oc.ijk_driven(p["t1"], p["t2"], p["g_abij"], p["g_aijk"], p["g_abci"], p["eps_occ"], p["eps_vir"])
+    n = o * (o + 1) * (o + 2) // 6 - o
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_plan_rank_main, args=(r, 2, port, o, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = dict(q.get(timeout=180) for _ in procs)
+    for pr in procs:
+        pr.join(timeout=60)
+    for r in range(2):
+        for panel_block, e, gathered in res[r]:
+            assert abs(e - ref) < 1e-12
+            assert sorted(gathered[0] + gathered[1]) == list(range(n))          # a partition of the job
+            if panel_block == 0:
+                assert gathered[0] == list(range(0, n, 2)) and gathered[1] == list(range(1, n, 2))
+            else:
+                assert abs(len(gathered[0]) - len(gathered[1])) <= 8            # groups of <= 8 units, dealt greedily
+
+
+def test_library_shard_plan_properties():
+    from mpqc_b200 import lib as L
+    lib = L.load()
+    o, n = 21, 1750
+    for W in (1, 2, 4, 8):
+        # one process driving W GPUs: static 7/8 (a multiple of W), the rest is the work-stealing tail
+        shards = [_shard(lib, o, W, r, 1, 0) for r in range(W)]
+        tail = shards[0][1]
+        assert tail == (n if W == 1 else (n // 8) * 7 // W * W) and all(t == tail for _, t in shards)
+        assert sorted(sum((s for s, _ in shards), [])) == list(range(tail))
+        # panel-cache mode: whole occupied-block groups per worker, no tail, balanced within one group
+        ps = [_shard(lib, o, W, r, 1, 4)[0] for r in range(W)]
+        assert sorted(sum(ps, [])) == list(range(n))
+        assert max(len(s) for s in ps) - min(len(s) for s in ps) <= 64
+        i, j, k = (__import__("ctypes").c_int32() for _ in range(3))
+        keys_of = []
+        for s in ps:
+            ks = set()
+            for u in s:
+                lib.mpqc_t_triple_of_unit(o, u, i, j, k)
+                ks.add((i.value // 4, j.value // 4, k.value // 4))
+            keys_of.append(ks)
+        for a in range(W):
+            for b in range(a + 1, W):
+                assert not (keys_of[a] & keys_of[b])                             # a group never straddles two workers
+    # a sub-job (first, stride, count) and bad arguments
+    mine, _ = _shard(lib, o, 3, 1, 0, 0, first=5, stride=2, count=100)
+    assert mine == list(range(1, 100, 3))
+    assert lib.mpqc_t_shard_plan(o, 0, 1, -1, 2, 2, 0, 0, None, 0, None) == -1
+
+
 def test_dump_roundtrip_and_h2o_fixture(tmp_path):
     from mpqc_b200 import dump
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "h2o_631g.npz"))
