@@ -356,7 +356,8 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(args.workload, {}).get("w_contract_dram_bytes_per_launch")
+            per_triple = json.load(open(tpath)).get(args.workload, {}).get("w_contract_dram_bytes_per_triple")
+            traffic = per_triple * (per_launch_flops / unit_flops) if per_triple else None   # ncu figure x triples per launch
         except Exception:
             traffic = None
     roofline = {"kernel": "w_contract_dmma_kernel", "bound": "tensor", "achieved": achieved, "peak": tf_peak.value,

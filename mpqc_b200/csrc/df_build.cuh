@@ -280,26 +280,61 @@ int ensure_panels(mpqc_t_handle* h, const std::vector<int>& need, int64_t* launc
   for (int x : need) wanted[(size_t)x] = 1;
   ++h->stamp;
   bool changed = false;
-  for (int x : need) {
-    int s = h->slot_of[(size_t)x];
-    if (s < 0) {
-      // victim: a free slot, else the least recently used slot whose panel is not needed by this group
-      int victim = -1;
-      for (int q = 0; q < h->npanel; ++q) {
-        const int xq = h->x_of_slot[(size_t)q];
-        if (xq < 0) { victim = q; break; }
-        if (wanted[(size_t)xq]) continue;
-        if (victim < 0 || h->slot_stamp[(size_t)q] < h->slot_stamp[(size_t)victim]) victim = q;
-      }
-      MPQC_T_CHECK(victim >= 0, MPQC_T_ERR_INTERNAL, "no evictable panel slot");
-      if (h->x_of_slot[(size_t)victim] >= 0) h->slot_of[(size_t)h->x_of_slot[(size_t)victim]] = -1;
-      h->x_of_slot[(size_t)victim] = x;
-      h->slot_of[(size_t)x] = victim;
-      MPQC_T_TRY(build_panels(h, x, 1, victim, launches));
-      s = victim;
-      changed = true;
+  auto evictable = [&](int q) {
+    const int xq = h->x_of_slot[(size_t)q];
+    return xq < 0 || !wanted[(size_t)xq];
+  };
+  auto assign = [&](int x, int slot) {
+    if (h->x_of_slot[(size_t)slot] >= 0) h->slot_of[(size_t)h->x_of_slot[(size_t)slot]] = -1;
+    h->x_of_slot[(size_t)slot] = x;
+    h->slot_of[(size_t)x] = slot;
+    h->slot_stamp[(size_t)slot] = h->stamp;
+    changed = true;
+  };
+  // missing panels, as runs of consecutive occupied indices (a group's missing panels are usually one whole block)
+  for (size_t a = 0; a < need.size();) {
+    if (h->slot_of[(size_t)need[a]] >= 0) {
+      h->slot_stamp[(size_t)h->slot_of[(size_t)need[a]]] = h->stamp;
+      ++a;
+      continue;
     }
-    h->slot_stamp[(size_t)s] = h->stamp;
+    size_t b = a + 1;
+    while (b < need.size() && need[b] == need[b - 1] + 1 && h->slot_of[(size_t)need[b]] < 0) ++b;
+    const int len = (int)(b - a);
+    // a window of `len` consecutive evictable slots lets the run be built by ONE flattened-row GEMM (build_panels);
+    // among the candidates take the one whose most recently used slot is oldest (free slots count as oldest)
+    int best = -1;
+    int64_t best_age = 0;
+    for (int s0 = 0; len > 1 && s0 + len <= h->npanel; ++s0) {
+      int64_t newest = -1;
+      bool ok = true;
+      for (int t = 0; t < len && ok; ++t) {
+        ok = evictable(s0 + t);
+        if (ok && h->x_of_slot[(size_t)(s0 + t)] >= 0) newest = std::max(newest, h->slot_stamp[(size_t)(s0 + t)]);
+      }
+      if (ok && (best < 0 || newest < best_age)) {
+        best = s0;
+        best_age = newest;
+      }
+    }
+    if (best >= 0) {
+      for (int t = 0; t < len; ++t) assign(need[a + (size_t)t], best + t);
+      MPQC_T_TRY(build_panels(h, need[a], len, best, launches));
+    } else {
+      // one panel at a time: a free slot, else the least recently used slot whose panel this group does not need
+      for (size_t c = a; c < b; ++c) {
+        int victim = -1;
+        for (int q = 0; q < h->npanel; ++q) {
+          if (!evictable(q)) continue;
+          if (h->x_of_slot[(size_t)q] < 0) { victim = q; break; }
+          if (victim < 0 || h->slot_stamp[(size_t)q] < h->slot_stamp[(size_t)victim]) victim = q;
+        }
+        MPQC_T_CHECK(victim >= 0, MPQC_T_ERR_INTERNAL, "no evictable panel slot");
+        assign(need[c], victim);
+        MPQC_T_TRY(build_panels(h, need[c], 1, victim, launches));
+      }
+    }
+    a = b;
   }
   if (changed)   // pageable source: the runtime stages it before returning, so slot_of may change again right away
     MPQC_T_CUDA(cudaMemcpyAsync(h->slot_map_dev, h->slot_of.data(), (size_t)h->o * sizeof(int), cudaMemcpyHostToDevice,
