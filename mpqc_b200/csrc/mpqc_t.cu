@@ -513,6 +513,24 @@ static int comm_member_init(CommMember& m) {
   return MPQC_T_OK;
 }
 
+// One tiny all-reduce and all-gather per member right after the communicator exists: NCCL sets up its peer
+// connections lazily on the first collective of each kind, which otherwise costs the first (T) call ~0.5 s.
+static int comm_member_warmup(const CommMember& m, int nranks) {
+  if (nranks <= 1 || !m.comm) return MPQC_T_OK;
+  const NcclApi& nc = nccl_api();
+  MPQC_T_CUDA(cudaSetDevice(m.device));
+  cudaStream_t st = nullptr;
+  MPQC_T_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  int rc = cuda_status(cudaMemsetAsync(m.scratch, 0, (size_t)(nranks + 1) * sizeof(double), st), "cudaMemsetAsync", __FILE__, __LINE__);
+  if (rc == MPQC_T_OK)
+    rc = nccl_status(nc.AllReduce(m.scratch, m.scratch, 1, kNcclFloat64, kNcclSum, m.comm, st), "ncclAllReduce(warm-up)", __FILE__, __LINE__);
+  if (rc == MPQC_T_OK)
+    rc = nccl_status(nc.AllGather(m.scratch + m.rank, m.scratch, 1, kNcclFloat64, m.comm, st), "ncclAllGather(warm-up)", __FILE__, __LINE__);
+  if (rc == MPQC_T_OK) rc = cuda_status(cudaStreamSynchronize(st), "cudaStreamSynchronize(warm-up)", __FILE__, __LINE__);
+  cudaStreamDestroy(st);
+  return rc;
+}
+
 int mpqc_t_comm_create_rank(mpqc_t_comm** out, int32_t nranks, int32_t rank, const mpqc_t_unique_id* id, int32_t device) {
   MPQC_T_CHECK(out != nullptr, MPQC_T_ERR_BAD_ARG, "communicator pointer is NULL");
   *out = nullptr;
@@ -537,6 +555,7 @@ int mpqc_t_comm_create_rank(mpqc_t_comm** out, int32_t nranks, int32_t rank, con
       NcclUniqueId uid;
       memcpy(&uid, id, sizeof(uid));
       rc = nccl_status(nc.CommInitRank(&c->members[0].comm, nranks, uid, rank), "ncclCommInitRank", __FILE__, __LINE__);
+      if (rc == MPQC_T_OK) rc = comm_member_warmup(c->members[0], nranks);
     }
   }
   if (rc != MPQC_T_OK) {
@@ -594,6 +613,20 @@ int mpqc_t_comm_create_local(mpqc_t_comm** out, int32_t ngpu, const int32_t* dev
       std::vector<NcclApi::comm_t> comms(ngpu, nullptr);
       rc = nccl_status(nc.CommInitAll(comms.data(), ngpu, devs.data()), "ncclCommInitAll", __FILE__, __LINE__);
       for (int g = 0; g < ngpu; ++g) c->members[g].comm = comms[g];
+      if (rc == MPQC_T_OK) {   // warm-up collectives, one thread per member (each blocks until all have joined)
+        std::vector<std::thread> th;
+        for (int g = 0; g < ngpu; ++g)
+          th.emplace_back([&, g] {
+            rcs[g] = comm_member_warmup(c->members[g], ngpu);
+            if (rcs[g] != MPQC_T_OK) msgs[g] = last_error_string();
+          });
+        for (auto& t : th) t.join();
+        for (int g = 0; g < ngpu && rc == MPQC_T_OK; ++g)
+          if (rcs[g] != MPQC_T_OK) {
+            last_error_string() = msgs[g];
+            rc = rcs[g];
+          }
+      }
     }
   }
   if (rc != MPQC_T_OK) {
