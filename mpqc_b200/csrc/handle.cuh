@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "host_util.cuh"
@@ -145,6 +146,10 @@ int ensure_units(mpqc_t_handle* h, int64_t n) {
 }
 
 int auto_batch(const mpqc_t_handle* h) {
+  if (const char* env = getenv("MPQC_T_BATCH")) {   // A/B runs only (scripts/sweep.py, bench.py)
+    const int b = atoi(env);
+    if (b > 0) return b;
+  }
   int64_t tiles_per_triple = 3LL * h->nmt * h->nnt;
   // >= 128 waves of tiles per launch keeps the persistent grid's tail (half a tile per SM) and the per-launch gaps
   // under ~0.5 %.  Measured (scripts/sweep.py, round 2): larger batches are monotonically better at every shape
