@@ -60,7 +60,8 @@ inline const NcclApi& nccl_api() {
 }
 
 constexpr int kNcclFloat64 = 8;   // ncclDouble
-constexpr int kNcclSum = 0;
+constexpr int kNcclSum = 0;      // ncclRedOp_t
+constexpr int kNcclMin = 3;
 constexpr size_t kCommScratchDoubles = size_t(1) << 20;   // 8 MB per device: status words + chunks of the unit-energy vector
 
 inline int nccl_status(int r, const char* what, const char* file, int line) {

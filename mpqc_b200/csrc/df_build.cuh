@@ -177,8 +177,33 @@ int upload_df_impl(mpqc_t_handle* h, const mpqc_t_df_problem* p, bool on_device,
       npanel = (int)std::min<int64_t>(o, std::max(3, std::min(24, fit / 3 * 3)));
     }
   }
+  if (cv.nranks > 1) {
+    // the choice depends on this device's free memory, and it decides how the job is sharded (by unit or by panel
+    // group): all ranks must take the SAME one -- the smallest pool any rank asks for
+    double np = (double)npanel;
+    MPQC_T_TRY(allreduce_host_vector(cv, &np, 1, st, kNcclMin));
+    npanel = (int)(np + 0.5);
+  }
   const bool panel_mode = npanel < o;
-  MPQC_T_TRY(alloc_operands(h, npanel, factors + staging + (panel_mode || !on_device ? t2_bytes : 0.0)));
+  // all allocations of this upload, then an agreement among the ranks, before the first input collective
+  DevBuf xijt;
+  const size_t arena_need = staged_size((size_t)v * o, on_device, 1) + staged_size((size_t)v * v * o * o, on_device, cv.nranks) +
+                            staged_size((size_t)naux * v * v, on_device, cv.nranks) +
+                            staged_size((size_t)naux * o * o, on_device, 1) + staged_size((size_t)naux * v * o, on_device, cv.nranks);
+  const int rc_alloc = [&]() -> int {
+    const double arena_new = arena_need > h->arena_cap ? (double)arena_need * 8.0 : 0.0;
+    MPQC_T_TRY(alloc_operands(h, npanel, factors + arena_new + (panel_mode ? t2_bytes : 0.0)));
+    MPQC_T_TRY(arena_reserve(h, arena_need));
+    MPQC_T_CUDA(cudaMalloc(&h->XaiT, (size_t)o * v * Kx * sizeof(double)));
+    MPQC_T_CUDA(cudaMalloc(&h->XabT, (size_t)v * v * Kx * sizeof(double)));
+    MPQC_T_TRY(xijt.alloc((size_t)o * o * Kx));
+    if (panel_mode) {
+      MPQC_T_CUDA(cudaMalloc(&h->T2raw, (size_t)v * v * o * o * sizeof(double)));
+      MPQC_T_CUDA(cudaMalloc(&h->slot_map_dev, (size_t)o * sizeof(int)));
+    }
+    return MPQC_T_OK;
+  }();
+  MPQC_T_TRY(agree(cv, rc_alloc, st, "another rank of the (T) communicator could not allocate its operand memory"));
   MPQC_T_CUDA(cudaMemsetAsync(h->A, 0, (size_t)npanel * v * v * Kp * sizeof(double), st));
   if (h->flat) MPQC_T_CUDA(cudaMemsetAsync(h->AT, 0, (size_t)npanel * v * v * Kp * sizeof(double), st));
   MPQC_T_CUDA(cudaMemsetAsync(h->B, 0, (size_t)o * o * v * Kp * sizeof(double), st));
@@ -188,14 +213,9 @@ int upload_df_impl(mpqc_t_handle* h, const mpqc_t_df_problem* p, bool on_device,
   MPQC_T_CUDA(cudaMemcpyAsync(h->eps_occ, p->eps_occ, o * sizeof(double), kind, st));
   MPQC_T_CUDA(cudaMemcpyAsync(h->eps_vir, p->eps_vir, v * sizeof(double), kind, st));
   if (!on_device) h2d += (o + v) * 8;
-  DevBuf xijt;
   {
     Staged t1, t2, xab, xij, xai;
     CommView solo;
-    MPQC_T_TRY(arena_reserve(h, staged_size((size_t)v * o, on_device, 1) + staged_size((size_t)v * v * o * o, on_device, cv.nranks) +
-                                    staged_size((size_t)naux * v * v, on_device, cv.nranks) +
-                                    staged_size((size_t)naux * o * o, on_device, 1) +
-                                    staged_size((size_t)naux * v * o, on_device, cv.nranks)));
     MPQC_T_TRY(stage_in(h, t1, p->t1, (size_t)v * o, on_device, solo, st, &h2d));
     MPQC_T_TRY(stage_in(h, t2, p->t2, (size_t)v * v * o * o, on_device, cv, st, &h2d));
     MPQC_T_TRY(stage_in(h, xab, p->x_ab, (size_t)naux * v * v, on_device, cv, st, &h2d));
@@ -206,9 +226,6 @@ int upload_df_impl(mpqc_t_handle* h, const mpqc_t_df_problem* p, bool on_device,
       t_copy += now_s() - tc;
     }
     // factor copies with the auxiliary index fastest (one 128-byte TMA box row per 16 K), zero padded to Kx
-    MPQC_T_CUDA(cudaMalloc(&h->XaiT, (size_t)o * v * Kx * sizeof(double)));
-    MPQC_T_CUDA(cudaMalloc(&h->XabT, (size_t)v * v * Kx * sizeof(double)));
-    MPQC_T_TRY(xijt.alloc((size_t)o * o * Kx));
     MPQC_T_CUDA(cudaMemsetAsync(h->XaiT, 0, (size_t)o * v * Kx * sizeof(double), st));
     MPQC_T_CUDA(cudaMemsetAsync(h->XabT, 0, (size_t)v * v * Kx * sizeof(double), st));
     MPQC_T_CUDA(cudaMemsetAsync(xijt.p, 0, (size_t)o * o * Kx * sizeof(double), st));
@@ -224,9 +241,7 @@ int upload_df_impl(mpqc_t_handle* h, const mpqc_t_df_problem* p, bool on_device,
     MPQC_T_TRY(launch_transpose(st, t2.ptr, h->B, v, v, o * o, 1, v * Kp, 0, Kp, &launches));
     if (panel_mode) {
       // the hole part of a panel is written when the panel is built: keep t2 on the device
-      MPQC_T_CUDA(cudaMalloc(&h->T2raw, (size_t)v * v * o * o * sizeof(double)));
       MPQC_T_CUDA(cudaMemcpyAsync(h->T2raw, t2.ptr, (size_t)v * v * o * o * sizeof(double), cudaMemcpyDeviceToDevice, st));
-      MPQC_T_CUDA(cudaMalloc(&h->slot_map_dev, (size_t)o * sizeof(int)));
     } else {   // resident: hole part of every panel now; AT is copied from the finished panels in build_panels
       MPQC_T_TRY(launch_copy_hole(st, t2.ptr, h->A, v * v, o, o, v, v * Kp, Kp, v * v * Kp, v, -1.0, &launches));
     }

@@ -11,33 +11,6 @@
 
 namespace {
 
-// sum-all-reduce of n doubles held on the host through the member's pre-allocated device scratch (chunked), so the
-// collective itself never allocates.  Result overwrites x on every rank.
-int allreduce_host_vector(const CommView& cv, double* x, size_t n, cudaStream_t st) {
-  const NcclApi& nc = nccl_api();
-  for (size_t c0 = 0; c0 < n; c0 += kCommScratchDoubles) {
-    const size_t cn = std::min(kCommScratchDoubles, n - c0);
-    MPQC_T_CUDA(cudaMemcpyAsync(cv.scratch, x + c0, cn * sizeof(double), cudaMemcpyHostToDevice, st));
-    MPQC_T_NCCL(nc.AllReduce(cv.scratch, cv.scratch, cn, kNcclFloat64, kNcclSum, cv.comm, st));
-    MPQC_T_CUDA(cudaMemcpyAsync(x + c0, cv.scratch, cn * sizeof(double), cudaMemcpyDeviceToHost, st));
-    MPQC_T_CUDA(cudaStreamSynchronize(st));
-  }
-  return MPQC_T_OK;
-}
-
-// Agreement on a status among all ranks: returns the number of ranks that reported a failure (or -1 when the
-// collective itself failed).  Every rank calls it at the same points, whatever happened locally, so a rank that ran
-// out of memory makes the others return an error instead of leaving them blocked in a later collective.
-int count_failed_ranks(const CommView& cv, int local_rc, cudaStream_t st) {
-  if (cv.nranks <= 1) return local_rc != MPQC_T_OK ? 1 : 0;
-  double flag = local_rc != MPQC_T_OK ? 1.0 : 0.0;
-  const std::string keep = last_error_string();
-  int rc = allreduce_host_vector(cv, &flag, 1, st);
-  if (local_rc != MPQC_T_OK) last_error_string() = keep;
-  if (rc != MPQC_T_OK) return -1;
-  return (int)(flag + 0.5);
-}
-
 int validate_problem(const mpqc_t_problem* p) {
   MPQC_T_CHECK(p != nullptr, MPQC_T_ERR_BAD_ARG, "problem is NULL");
   MPQC_T_CHECK(p->o >= 1 && p->v >= 1, MPQC_T_ERR_BAD_ARG, "o and v must be >= 1");

@@ -151,11 +151,12 @@ int auto_batch(const mpqc_t_handle* h) {
     if (b > 0) return b;
   }
   int64_t tiles_per_triple = 3LL * h->nmt * h->nnt;
-  // >= 128 waves of tiles per launch keeps the persistent grid's tail (half a tile per SM) and the per-launch gaps
-  // under ~0.5 %.  Measured (scripts/sweep.py, round 2): larger batches are monotonically better at every shape
-  // (benzene 18.9 / 22.6 / 24.4 / 26.0 TFLOP/s at batch 2 / 5 / 16 / 47; trimer 32.36 / 32.55 / 32.64 at 1 / 2 / 4) --
-  // small batches that would keep W in L2 for the energy kernel lose more to launch gaps and tail waves than they gain.
-  int64_t nb = (128LL * h->num_sms + tiles_per_triple - 1) / tiles_per_triple;
+  // >= 256 waves of tiles per launch keeps the persistent grid's tail (half a tile per SM) and the per-launch gaps
+  // small.  Measured (round 2): larger batches are monotonically better at every shape -- benzene 18.9 / 22.6 / 24.4 /
+  // 26.0 TFLOP/s at batch 2 / 5 / 16 / 47 (scripts/sweep.py, profiles/r02_batch_sweep.txt); trimer bench on one box
+  // 32.47 / 32.59 / 32.65 at batch 2 / 4 / 8 (profiles/r02_ab_batch.txt).  Small batches that would keep W in L2 for
+  // the energy kernel lose more to launch gaps and tail waves than they gain.
+  int64_t nb = (256LL * h->num_sms + tiles_per_triple - 1) / tiles_per_triple;
   nb = std::max<int64_t>(1, std::min<int64_t>(nb, 1024));
   // bound the W workspace to ~6 GB
   size_t per = (size_t)3 * h->v * h->v * h->ldw * sizeof(double);

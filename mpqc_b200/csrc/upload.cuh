@@ -43,6 +43,43 @@ int replicate_from_host(const CommView& cv, double* dst, const double* src, size
   return rc;
 }
 
+// sum-all-reduce of n doubles held on the host through the member's pre-allocated device scratch (chunked), so the
+// collective itself never allocates.  Result overwrites x on every rank.
+int allreduce_host_vector(const CommView& cv, double* x, size_t n, cudaStream_t st, int op = kNcclSum) {
+  const NcclApi& nc = nccl_api();
+  for (size_t c0 = 0; c0 < n; c0 += kCommScratchDoubles) {
+    const size_t cn = std::min(kCommScratchDoubles, n - c0);
+    MPQC_T_CUDA(cudaMemcpyAsync(cv.scratch, x + c0, cn * sizeof(double), cudaMemcpyHostToDevice, st));
+    MPQC_T_NCCL(nc.AllReduce(cv.scratch, cv.scratch, cn, kNcclFloat64, op, cv.comm, st));
+    MPQC_T_CUDA(cudaMemcpyAsync(x + c0, cv.scratch, cn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    MPQC_T_CUDA(cudaStreamSynchronize(st));
+  }
+  return MPQC_T_OK;
+}
+
+// Agreement on a status among all ranks: returns the number of ranks that reported a failure (or -1 when the
+// collective itself failed).  Every rank calls it at the same points, whatever happened locally, so a rank that ran
+// out of memory makes the others return an error instead of leaving them blocked in a later collective.
+int count_failed_ranks(const CommView& cv, int local_rc, cudaStream_t st) {
+  if (cv.nranks <= 1) return local_rc != MPQC_T_OK ? 1 : 0;
+  double flag = local_rc != MPQC_T_OK ? 1.0 : 0.0;
+  const std::string keep = last_error_string();
+  int rc = allreduce_host_vector(cv, &flag, 1, st);
+  if (local_rc != MPQC_T_OK) last_error_string() = keep;
+  if (rc != MPQC_T_OK) return -1;
+  return (int)(flag + 0.5);
+}
+
+// Every rank calls this at the same point, right after its allocations and before the first input collective: returns
+// the local error if there is one, an error if ANY peer failed, MPQC_T_OK otherwise -- so a rank that ran out of memory
+// inside an upload makes all ranks return instead of leaving its peers blocked in an all-gather.
+int agree(const CommView& cv, int local_rc, cudaStream_t st, const char* what) {
+  const int nfail = count_failed_ranks(cv, local_rc, st);
+  if (local_rc != MPQC_T_OK) return local_rc;
+  if (nfail != 0) return fail(nfail < 0 ? MPQC_T_ERR_NCCL : MPQC_T_ERR_INTERNAL, what, __FILE__, __LINE__);
+  return MPQC_T_OK;
+}
+
 // host tensor -> device copy in the handle's staging arena (sharded + all-gathered when a communicator is present), or
 // an alias of a device pointer
 struct Staged {
@@ -81,9 +118,14 @@ int upload_impl(mpqc_t_handle* h, const mpqc_t_problem* p, bool on_device, const
                                             staged_size((size_t)v * o * o * o, false, cv.nranks) +
                                             2 * arena_round(padded_count((size_t)slab * row, cv.nranks));
   const double arena_new = arena_need > h->arena_cap ? (double)arena_need * 8.0 : 0.0;
-  // dense inputs: all o panels resident
-  MPQC_T_TRY(alloc_operands(h, (int)o, arena_new));
-  MPQC_T_TRY(arena_reserve(h, arena_need));
+  // dense inputs: all o panels resident.  All allocations of this upload happen here, followed by an agreement among
+  // the ranks, before the first input collective.
+  const int rc_alloc = [&]() -> int {
+    MPQC_T_TRY(alloc_operands(h, (int)o, arena_new));
+    MPQC_T_TRY(arena_reserve(h, arena_need));
+    return MPQC_T_OK;
+  }();
+  MPQC_T_TRY(agree(cv, rc_alloc, st, "another rank of the (T) communicator could not allocate its operand memory"));
   // Ordering contract (include/mpqc_t.h): device-resident inputs may have been produced on any stream of the caller;
   // the handle's stream is non-blocking, so wait for the whole device before reading them.
   if (on_device) MPQC_T_CUDA(cudaDeviceSynchronize());
