@@ -26,6 +26,7 @@
 #include <thread>
 #include <vector>
 
+#include "mpqc/chemistry/qc/lcao/cc/ccsd_t_gpu_densify.h"
 #include "mpqc/util/core/exception.h"
 #include "mpqc/util/misc/time.h"
 #include "mpqc_t.h"  // include/mpqc_t.h of the mpqc_b200 repository
@@ -78,59 +79,12 @@ class HostBuffer {
   std::size_t n_ = 0;
 };
 
-/// copies one tile into its place in the dense row-major buffer: contiguous runs along the last dimension, offsets
-/// advanced by an odometer over the leading dimensions (no per-element N-d index arithmetic)
-template <typename Tile>
-void scatter_tile(const Tile &tile, const std::vector<std::size_t> &stride, double *out) {
-  const auto &range = tile.range();
-  const std::size_t rank = range.rank();
-  const auto lo = range.lobound();
-  const auto ext = range.extent();
-  const std::size_t run = ext[rank - 1];
-  std::size_t base = 0, nrun = 1;
-  for (std::size_t d = 0; d < rank; ++d) base += std::size_t(lo[d]) * stride[d];
-  for (std::size_t d = 0; d + 1 < rank; ++d) nrun *= ext[d];
-  std::vector<std::size_t> idx(rank, 0);
-  const double *src = tile.data();
-  std::size_t off = base;
-  for (std::size_t r = 0; r < nrun; ++r) {
-    std::memcpy(out + off, src, run * sizeof(double));
-    src += run;
-    // odometer over dimensions rank-2 .. 0
-    for (std::size_t d = rank - 1; d-- > 0;) {
-      off += stride[d];
-      if (++idx[d] < std::size_t(ext[d])) break;
-      off -= stride[d] * ext[d];
-      idx[d] = 0;
-    }
-  }
-}
-
-/// gathers a (possibly sparse-policy, distributed) array into one dense row-major host buffer on every rank; zero
-/// tiles of a sparse-policy array stay zero (sparse_threshold 1e-20, mpqc_task.cpp:23-24).  Replication idiom of
-/// math/tensor/clr/cp_als.h:83-84; tiles are scattered by a few host threads (disjoint destinations).
+/// gathers a (possibly sparse-policy, distributed) array into one dense row-major host buffer in page-locked memory on
+/// every rank (ccsd_t_gpu_densify.h does the tile scatter)
 template <typename Tile, typename Policy>
 HostBuffer densify(TA::DistArray<Tile, Policy> array) {
-  auto &world = array.world();
-  array.make_replicated();
-  world.gop.fence();
-  const auto &trange = array.trange();
-  const auto &erange = trange.elements_range();
-  const std::size_t rank = erange.rank();
-  const auto ext = erange.extent();
-  std::vector<std::size_t> stride(rank, 1);
-  for (std::size_t d = rank - 1; d > 0; --d) stride[d - 1] = stride[d] * std::size_t(ext[d]);
-  HostBuffer out(erange.volume());
-  std::memset(out.data(), 0, out.size() * sizeof(double));
-  std::vector<Tile> tiles;
-  for (auto it = array.begin(); it != array.end(); ++it) tiles.push_back(it->get());
-  const std::size_t nthread = std::max<std::size_t>(1, std::min<std::size_t>(8, std::thread::hardware_concurrency()));
-  std::vector<std::thread> pool;
-  for (std::size_t t = 0; t < nthread; ++t)
-    pool.emplace_back([&, t] {
-      for (std::size_t i = t; i < tiles.size(); i += nthread) scatter_tile(tiles[i], stride, out.data());
-    });
-  for (auto &th : pool) th.join();
+  HostBuffer out(array.trange().elements_range().volume());
+  densify_into(array, out.data());
   return out;
 }
 

@@ -224,13 +224,17 @@ class CCSD_T:
         self.n_laplace_quad_ = int(kv.get("quadrature_points", 4))                # :131
         self.verbose_ = bool(kv.get("verbose", False))
         # GPU-path keywords
+        # (the in-class patch of the reference spells them ngpu / gpu_batch / gpu_df / gpu_dump_file; both spellings work)
         self.ngpu_ = int(kv.get("ngpu", 1))
         self.device_ids_ = kv.get("device_ids")
-        self.batch_ = int(kv.get("batch", 0))
+        self.batch_ = int(kv.get("gpu_batch", kv.get("batch", 0)))
         self.use_nccl_ = bool(kv.get("use_nccl", False))
-        # "df_direct": with a density-fitted CCSD (method df) assemble the integrals on the device from the
-        # three-centre factors instead of receiving the dense <ia|bc> tensor
-        self.df_direct_ = bool(kv.get("df_direct", False))
+        # "gpu_df" / "df_direct": with a density-fitted CCSD (method df) assemble the integrals on the device from the
+        # three-centre factors instead of receiving the dense <ia|bc> tensor.  Off by default in this
+        # mirror so that tests choose the input form explicitly (the patched reference defaults to on when is_df()).
+        self.df_direct_ = bool(kv.get("gpu_df", kv.get("df_direct", False)))
+        self.df_block_ = int(kv.get("gpu_df_block", 0))      # 0 automatic, -1 resident, b > 0 panel cache (mpqc_t_options.df_block)
+        self.dump_file_ = str(kv.get("gpu_dump_file", ""))
         self.rank_ = int(kv.get("rank", 0))
         self.world_size_ = int(kv.get("world_size", 1))
         if self.ngpu_ < 1:
@@ -323,7 +327,11 @@ class CCSD_T:
         opt.unit_stride = self.world_size_
         opt.unit_count = -1
         opt.batch = self.batch_
+        opt.df_block = self.df_block_
         opt.use_nccl = 1 if self.use_nccl_ else 0
+        if self.dump_file_ and not use_df and isinstance(eps, np.ndarray):
+            from . import dump                                  # same MPQCT001 file the patched reference writes
+            dump.save_problem(self.dump_file_, eps, n_frozen, cc.t1(), cc.t2(), cc.get_abij(), cc.get_aijk(), cc.get_abci())
         st = L.Stats()
         e = C.c_double(0.0)
         lib = L.load()

@@ -94,6 +94,12 @@ class DistArray {
   const TiledRange& trange() const { return tr_; }
   const_iterator begin() const { return f_.data(); }
   const_iterator end() const { return f_.data() + f_.size(); }
+  // mock only: lets a test build an array from explicit tiles (zero tiles of a sparse array are simply absent)
+  void mock_set(const TiledRange& tr, const std::vector<Tile>& tiles) {
+    tr_ = tr;
+    f_.clear();
+    for (const Tile& t : tiles) f_.push_back(Future<Tile>{t});
+  }
  private:
   TiledRange tr_;
   std::vector<Future<Tile>> f_;

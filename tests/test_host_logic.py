@@ -27,6 +27,18 @@ def test_keyval_keywords_and_defaults():
     assert not w.reblock_ and not w.reblock_inner_ and w.n_laplace_quad_ == 3      # ccsd_t.h:125-128
 
 
+def test_gpu_keywords_follow_the_patched_reference():
+    # integration/mpqc_ccsd_t_gpu.patch adds ngpu / gpu_batch / gpu_df / gpu_dump_file to the reference's KeyVal table
+    w = CCSD_T({"type": "CCSD(T)", "ngpu": 2, "gpu_batch": 3, "gpu_df": True, "gpu_df_block": 4, "gpu_dump_file": "x.mpqct"})
+    assert (w.ngpu_, w.batch_, w.df_direct_, w.df_block_, w.dump_file_) == (2, 3, True, 4, "x.mpqct")
+    w = CCSD_T({"batch": 5, "df_direct": True})                 # round-1 spellings keep working
+    assert w.batch_ == 5 and w.df_direct_ and w.df_block_ == 0 and w.dump_file_ == ""
+    patch = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "integration",
+                              "mpqc_ccsd_t_gpu.patch")).read()
+    for key in ("ngpu", "gpu_batch", "gpu_df", "gpu_dump_file"):
+        assert f'"{key}"' in patch, key
+
+
 def test_invalid_approach_raises_input_error():
     with pytest.raises(InputError) as ei:
         CCSD_T({"type": "CCSD(T)", "approach": "medium"})

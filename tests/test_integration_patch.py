@@ -7,6 +7,7 @@ container; not the GPU box) and prove, against the REAL header:
   * the patched real ccsd_t.h + ccsd_t_gpu_impl.h type-check (g++ -std=c++14 -Wall -Werror) with mocks of TiledArray,
     MADNESS, Eigen and ccsd.h ONLY -- the CCSD_T class, its access specifiers and the exception classes are the
     reference's own files;
+  * the adapter's tile scatter (ccsd_t_gpu_densify.h) is RUN on the TiledArray mock and checked element by element;
   * the subclass route (round 1's adapter) cannot compile against the real header -- the reason for the in-class route;
   * every CCSD base-class member the GPU code touches is public or protected in the real ccsd.h;
   * the second caller (CCSD_T_F12) really calls the base's compute_ccsd_t().
@@ -35,7 +36,8 @@ def _tree(tmp_path, apply=True):
         shutil.copy(os.path.join(REF, CC, f), dst / CC / f)
     if apply:
         subprocess.run(["patch", "-p1", "-s", "-i", PATCH], cwd=dst, check=True)
-        shutil.copy(os.path.join(ROOT, "integration", "ccsd_t_gpu_impl.h"), dst / CC / "ccsd_t_gpu_impl.h")
+        for hdr in ("ccsd_t_gpu_impl.h", "ccsd_t_gpu_densify.h"):
+            shutil.copy(os.path.join(ROOT, "integration", hdr), dst / CC / hdr)
     return dst
 
 
@@ -55,7 +57,8 @@ def test_patch_applies_and_reverses_on_the_reference_tree(tmp_path):
     assert 'kv.value<std::string>("approach", "gpu")' in hdr            # the GPU path is the new default
     for cpu in ("coarse", "fine", "straight", "laplace"):               # the CPU approaches stay callable for A/B runs
         assert f'approach_ == "{cpu}"' in hdr
-    assert "ccsd_t_gpu_impl.h" in open(tree / CC / "CMakeLists.txt").read()
+    cm = open(tree / CC / "CMakeLists.txt").read()
+    assert "ccsd_t_gpu_impl.h" in cm and "ccsd_t_gpu_densify.h" in cm and "MPQC_T_CUDA_LIBRARY" in cm
     back = subprocess.run(["patch", "-p1", "-R", "--dry-run", "-i", PATCH], cwd=tree, capture_output=True, text=True)
     assert back.returncode == 0, back.stdout + back.stderr
 
@@ -81,6 +84,19 @@ def test_subclass_route_cannot_reach_the_private_getters(tmp_path):
     res = _gxx(tree, src)
     assert res.returncode != 0
     assert res.stderr.count("private within this context") >= 2, res.stderr[-2000:]
+
+
+def test_densify_scatters_tiles_correctly(tmp_path):
+    # the adapter's only non-trivial host logic -- DistArray tiles -> one dense row-major buffer with contiguous-run
+    # copies and an odometer -- is RUN here on the TiledArray mock: ranks 1..4, ragged tilings, a missing (zero) tile of a
+    # sparse-policy array, an <ia|bc>-shaped case; every element is compared with a brute-force N-d index walk
+    tree = _tree(tmp_path)
+    exe = tmp_path / "run_densify"
+    res = subprocess.run(["g++", "-std=c++14", "-O1", "-Wall", "-Werror", "-pthread", "-I", MOCK, "-I", str(tree / "src"),
+                          os.path.join(MOCK, "run_densify.cpp"), "-o", str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-3000:]
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0 and "densify: ok" in run.stdout, run.stdout + run.stderr
 
 
 def _access_of(header_text, class_name, member_regex):
