@@ -32,7 +32,7 @@ import numpy as np
 
 __all__ = [
     "straight", "coarse", "ijk_driven", "ijk_triple_list", "triple_weight",
-    "w_ijk", "v_ijk", "energy_ijk", "reduce_plain", "reduce_symm", "flops",
+    "w_ijk", "v_ijk", "energy_ijk", "reduce_plain", "reduce_symm", "flops", "vblock_energies",
 ]
 
 
@@ -280,3 +280,35 @@ def ijk_driven(t1, t2, g_abij, g_aijk, g_abci, eps_occ, eps_vir, triples=None,
     if return_parts:
         return e_total, np.asarray(parts)
     return e_total
+
+
+def vblock_energies(t1, t2, g_abij, g_aijk, g_abci, eps_occ, eps_vir, vir_block: int = 8):
+    """The SAME energy decomposed over virtual-block triples a >= b >= c but accumulated in the ijk-driven order -- the
+    identity behind ``mpqc_t_run_vblocks`` (include/mpqc_t.h):
+
+        e_block[tt] = sum_{i>=j>=k} w_ijk * sum_{(a,b,c) in orbit(tt)} (W+V) Z / D
+
+    where orbit(tt) is the union of the DISTINCT permutations of the three tiles (TA, TB, TC).  Because
+    sum_{ijk} f(abc, ijk) is symmetric in (a,b,c) and the orbit is closed under permutations, e_block[tt] equals what
+    iteration ``global_iter = tt + 1`` of the reference's coarse loop adds (ccsd_t.h:443-480, :619-638), including the
+    CCSD_T_ReduceSymm weights of the blocks with coinciding tiles.  Returns the list in global_iter order."""
+    o, v = len(eps_occ), len(eps_vir)
+    vb = _blocks(v, vir_block)
+    sets = [(a, b, c) for a in range(len(vb)) for b in range(a + 1) for c in range(b + 1)]
+    out = np.zeros(len(sets))
+    for (i, j, k) in ijk_triple_list(o):
+        w = w_ijk(t2, g_aijk, g_abci, i, j, k)
+        vv = v_ijk(t1, g_abij, i, j, k)
+        z = (4.0 * w + w.transpose(2, 0, 1) + w.transpose(1, 2, 0)
+             - 2.0 * (w.transpose(2, 1, 0) + w.transpose(0, 2, 1) + w.transpose(1, 0, 2)))
+        d = (eps_occ[i] + eps_occ[j] + eps_occ[k]
+             - eps_vir[:, None, None] - eps_vir[None, :, None] - eps_vir[None, None, :])
+        f = (w + vv) * z / d
+        wt = triple_weight(i, j, k)
+        for tt, tiles in enumerate(sets):
+            acc = 0.0
+            for perm in set(itertools.permutations(tiles)):
+                (a0, a1), (b0, b1), (c0, c1) = vb[perm[0]], vb[perm[1]], vb[perm[2]]
+                acc += float(f[a0:a1, b0:b1, c0:c1].sum())
+            out[tt] += wt * acc
+    return out

@@ -55,6 +55,19 @@ def test_golden_vectors(path):
     assert abs(oc.coarse(*_args(p)) - float(g["e_coarse"])) < TOL
 
 
+@pytest.mark.parametrize("o,v,block", [(4, 19, 8), (3, 10, 4), (5, 9, 3)])
+def test_virtual_block_decomposition_identity(o, v, block):
+    # the identity behind mpqc_t_run_vblocks, on the CPU: the ijk-driven accumulation, split over virtual-block triples,
+    # reproduces every iteration of the reference's coarse loop (plain blocks x2, ReduceSymm blocks, ragged last block)
+    p = make_problem(o, v, seed=70 + v)
+    args = (p["t1"], p["t2"], p["g_abij"], p["g_aijk"], p["g_abci"], p["eps_occ"], p["eps_vir"])
+    e_coarse, parts = oc.coarse(*args, vir_block=block, return_parts=True)
+    vb = oc.vblock_energies(*args, vir_block=block)
+    assert [g for g, _ in parts] == list(range(1, len(vb) + 1))
+    np.testing.assert_allclose(vb, [e for _, e in parts], atol=1e-13)
+    assert abs(vb.sum() - e_coarse) < 1e-13 and abs(vb.sum() - oc.ijk_driven(*args)) < 1e-13
+
+
 def test_round_robin_split_sums_to_total():
     # ccsd_t.h:477-480: rank r takes global_iter % size == r, partial energies add up (gop.sum :692)
     p = make_problem(3, 9)
