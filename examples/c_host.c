@@ -1,7 +1,7 @@
 /*
  * Minimal C host of the (T) library: shows that include/mpqc_t.h is a plain C ABI (no C++/torch types).
  * Builds with:  gcc -std=c99 -Iinclude examples/c_host.c -o c_host -Lmpqc_b200 -lmpqc_t_cuda -Wl,-rpath,$PWD/mpqc_b200
- * Reads an MPQCT001 dump (mpqc_b200/dump.py, integration/ccsd_t_gpu.h) and prints E(T).
+ * Reads an MPQCT001 dump (mpqc_b200/dump.py, integration/ccsd_t_gpu_impl.h) and prints E(T).
  * Exit code: 0 ok, 2 no CUDA device (mirrors mpqc's FeatureDisabled exit code, mpqc.cpp:261-264), 1 otherwise.
  */
 #include <stdio.h>

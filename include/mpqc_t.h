@@ -8,7 +8,8 @@
  *   /root/reference/src/mpqc/chemistry/qc/lcao/cc/ccsd_t.h:1127-1170 (straight)
  * i.e. everything between "T1/T2, orbital energies and the three integral classes are in hand"
  * and "a double comes back".  The MPQC-side adapter that gathers the TiledArray objects into the
- * dense buffers below is integration/ccsd_t_gpu.h.
+ * dense buffers below is integration/ccsd_t_gpu_impl.h, added to the reference's own class by
+ * integration/mpqc_ccsd_t_gpu.patch.
  *
  * Plain pointers and sizes only; no C++ or torch types; no exception crosses this boundary.
  * All arrays are IEEE double, dense, row-major (last index fastest), in exactly the layouts

@@ -5,7 +5,7 @@ same KeyVal keywords, same method names (``compute_ccsd_t``, ``evaluate``, ``tri
 ``obsolete``), same error behaviour (``InputError`` on an invalid ``approach``), same log lines --
 but the body of ``compute_ccsd_t`` hands the dense blocks through the C ABI of
 ``include/mpqc_t.h`` to the sm_100a kernels.  The compiled, MPQC-facing adapter with identical
-structure is ``integration/ccsd_t_gpu.h``; this Python mirror exists so that tests and
+structure is the in-class patch ``integration/mpqc_ccsd_t_gpu.patch`` + ``integration/ccsd_t_gpu_impl.h``; this Python mirror exists so that tests and
 ``bench.py`` exercise the same boundary without TiledArray/MADWorld.
 
 The CCSD base class of the reference (``ccsd.h:54-265``) is *not* rebuilt: it is represented by a

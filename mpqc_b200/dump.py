@@ -1,6 +1,6 @@
 """Tensor-dump format for replaying a real MPQC (T) without Libint.
 
-The adapter (integration/ccsd_t_gpu.h, ``dump_t_problem``) writes exactly what it hands to the C ABI; this module
+The adapter (integration/ccsd_t_gpu_impl.h, ``gpu_t::dump_problem``, keyword ``gpu_dump_file``) writes exactly what it hands to the C ABI; this module
 reads/writes the same file so a dump produced where MPQC is installed can be replayed here (tests, bench) and a
 fixture produced here (``oracle/h2o_golden.py``) can be loaded by a C++ host.
 
