@@ -118,12 +118,12 @@ def test_make_problem_validates_shapes():
                        p["g_aijk"], p["g_abci"])
 
 
-def _build_c_host(tmp_path):
+def _build_c_host(tmp_path, name="c_host"):
     import subprocess
-    exe = str(tmp_path / "c_host")
+    exe = str(tmp_path / name)
     libdir = os.path.join(ROOT, "mpqc_b200")
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
-                           os.path.join(ROOT, "examples", "c_host.c"), "-o", exe, "-L", libdir, "-lmpqc_t_cuda",
+                           os.path.join(ROOT, "examples", name + ".c"), "-o", exe, "-L", libdir, "-lmpqc_t_cuda",
                            f"-Wl,-rpath,{libdir}"])
     return exe
 
@@ -141,6 +141,15 @@ def test_plain_c_host_links_and_fails_loudly_without_gpu(lib, tmp_path):
     # the header is consumable from C99 and the library from a C program; without a device: exit code 2
     import subprocess
     exe = _build_c_host(tmp_path)
+    res = subprocess.run([exe, _h2o_dump(tmp_path)], capture_output=True, text=True)
+    assert res.returncode == 2 and "no CPU fallback" in res.stderr
+
+
+@pytest.mark.skipif(HAS_GPU, reason="CPU-box behaviour of the plain-C host")
+def test_plain_c_communicator_host_links_and_fails_loudly_without_gpu(lib, tmp_path):
+    # the communicator API (mpqc_t_comm_*, mpqc_t_energy_comm, mpqc_t_host_alloc) is consumable from C99 as well
+    import subprocess
+    exe = _build_c_host(tmp_path, "c_host_comm")
     res = subprocess.run([exe, _h2o_dump(tmp_path)], capture_output=True, text=True)
     assert res.returncode == 2 and "no CPU fallback" in res.stderr
 
